@@ -1,0 +1,100 @@
+"""ctypes binding of the C-ABI in include/gdft_b200.h.  No arithmetic here.
+
+The library is loaded lazily from the package directory (built in-tree by graddft_b200.build).  There
+is no CPU implementation behind these symbols and no fallback: a missing library, a missing symbol
+or a non-zero status raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / "libgdft_b200.so"
+
+GDFT_RHO, GDFT_GRAD, GDFT_TAU, GDFT_LAPL, GDFT_HF = 1, 2, 4, 8, 16
+OP_DENSITY_FWD, OP_DENSITY_BWD, OP_HF_FOCK, OP_ERI_J, OP_XC_INTEGRATE = 1, 2, 3, 4, 5
+PW_IDS = {
+    "LSDA_X": 0, "B88_X": 1, "VWN_C": 2, "LYP_C": 3, "PW92_C": 4, "B3LYP_SET": 5, "B88_SET": 6,
+    "DM21_INPUTS": 7, "DM21_LDA": 8, "DM21_GGA": 9, "DM21_MGGA": 10,
+}
+
+# name -> (restype, argtypes); mirrors include/gdft_b200.h one to one
+_P = c_void_p
+SIGNATURES = {
+    "gdft_version": (c_int, []),
+    "gdft_last_cuda_error": (c_int, []),
+    "gdft_status_string": (c_char_p, [c_int]),
+    "gdft_device_supported": (c_int, []),
+    "gdft_npad": (c_int64, [c_int64]),
+    "gdft_packed_basis_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "gdft_pack_basis": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, c_int]),
+    "gdft_pack_chi": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
+    "gdft_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64, c_int, c_int]),
+    "gdft_density_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "gdft_density_bwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "gdft_hf_fock": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t]),
+    "gdft_eri_jk": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "gdft_eri_j_transpose": (c_int, [_P, c_int64, _P, _P, _P, _P, c_size_t]),
+    "gdft_xc_integrate_fwd": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P, c_double, _P, _P, c_size_t]),
+    "gdft_xc_integrate_bwd": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P, c_double, _P, _P, _P, _P, c_size_t]),
+    "gdft_pointwise_ncols": (c_int, [c_int]),
+    "gdft_pointwise_fwd": (c_int, [_P, c_int64, c_int, c_double, _P, _P, _P, _P, _P]),
+    "gdft_pointwise_bwd": (c_int, [_P, c_int64, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gdft_fock_assemble": (c_int, [_P, c_int64, _P, _P, _P, c_double, _P]),
+    "gdft_fock_add_sym": (c_int, [_P, c_int64, _P, c_double, _P]),
+}
+
+_lib = None
+
+
+class GdftError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded C-ABI library; raises if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise GdftError(
+                f"{LIB_PATH} is missing: build it with `python -m graddft_b200.build` "
+                "(graddft_b200 has no CPU or eager fallback for its kernels)"
+            )
+        handle = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        L = lib()
+        msg = L.gdft_status_string(status).decode()
+        extra = f" (cuda error {L.gdft_last_cuda_error()})" if status == 4 else ""
+        raise GdftError(f"{what}: {msg}{extra}")
+
+
+def ptr(t: torch.Tensor | None):
+    """Device pointer of a contiguous float64 CUDA tensor (or NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise GdftError("graddft_b200 kernels need CUDA tensors (there is no CPU path)")
+    if t.dtype != torch.float64:
+        raise TypeError(f"expected float64, got {t.dtype}")
+    if not t.is_contiguous():
+        raise GdftError("tensor must be contiguous")
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

@@ -1,0 +1,366 @@
+// K3 (ERI sweep: Coulomb J, optional K, E_J), K6 (XC quadrature fwd/bwd) and the n x n predictor glue.
+// All of these are HBM-streaming kernels: 128-bit coalesced loads, warp-shuffle reductions, fixed-order
+// second-stage reductions (bitwise reproducible).
+#include "common.cuh"
+
+namespace gdft {
+
+// ---------------------------------------------------------------------------------------------------
+// J[row] = sum_col eri[row][col] P[col],  row = (p,q), col = (r,t)        grad_dft/molecule.py:811
+// 8 warps x 4 rows per CTA pass; P streamed through shared memory in 2048-double chunks so the
+// ERI stream is the only global traffic that matters.
+// ---------------------------------------------------------------------------------------------------
+constexpr int ERI_THREADS = 256;
+constexpr int ERI_ROWS_PER_WARP = 4;
+constexpr int ERI_ROWS_PER_CTA = 8 * ERI_ROWS_PER_WARP;
+constexpr int ERI_CHUNK = 2048;
+
+template <bool VEC>
+__global__ void __launch_bounds__(ERI_THREADS) eri_j_kernel(int64_t R, int64_t C, const double* __restrict__ eri,
+                                                           const double* __restrict__ P, double* __restrict__ J) {
+  __shared__ __align__(16) double sP[ERI_CHUNK];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t nblocks = (R + ERI_ROWS_PER_CTA - 1) / ERI_ROWS_PER_CTA;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t row_base = blk * ERI_ROWS_PER_CTA + warp * ERI_ROWS_PER_WARP;
+    double acc[ERI_ROWS_PER_WARP];
+    const double* rowp[ERI_ROWS_PER_WARP];
+#pragma unroll
+    for (int i = 0; i < ERI_ROWS_PER_WARP; i++) {
+      acc[i] = 0.0;
+      const int64_t row = row_base + i < R ? row_base + i : R - 1;  // clamp: duplicates are discarded below
+      rowp[i] = eri + row * C;
+    }
+    for (int64_t c0 = 0; c0 < C; c0 += ERI_CHUNK) {
+      const int len = (int)min((int64_t)ERI_CHUNK, C - c0);
+      __syncthreads();
+      for (int i = tid; i < len; i += ERI_THREADS) sP[i] = P[c0 + i];
+      __syncthreads();
+      if (VEC) {
+        const int len2 = len >> 1;  // C even => len even
+#pragma unroll 2
+        for (int i = lane; i < len2; i += 32) {
+          const double2 pv = reinterpret_cast<const double2*>(sP)[i];
+          double2 e[ERI_ROWS_PER_WARP];
+#pragma unroll
+          for (int q = 0; q < ERI_ROWS_PER_WARP; q++) e[q] = __ldcs(reinterpret_cast<const double2*>(rowp[q] + c0) + i);
+#pragma unroll
+          for (int q = 0; q < ERI_ROWS_PER_WARP; q++) acc[q] = fma(e[q].x, pv.x, fma(e[q].y, pv.y, acc[q]));
+        }
+      } else {
+#pragma unroll 2
+        for (int i = lane; i < len; i += 32) {
+          const double pv = sP[i];
+#pragma unroll
+          for (int q = 0; q < ERI_ROWS_PER_WARP; q++) acc[q] = fma(__ldcs(rowp[q] + c0 + i), pv, acc[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < ERI_ROWS_PER_WARP; q++) {
+      const double s = warp_sum(acc[q]);
+      if (lane == 0 && row_base + q < R) J[row_base + q] = s;
+    }
+  }
+}
+
+// Pbar[col] = sum_row Jbar[row] eri[row][col]; grid (col chunks, row splits) -> part[split][C]
+constexpr int ERIT_THREADS = 256;
+template <bool VEC>
+__global__ void __launch_bounds__(ERIT_THREADS) eri_jt_kernel(int64_t R, int64_t C, int64_t rows_per_split,
+                                                             const double* __restrict__ eri, const double* __restrict__ Jbar,
+                                                             double* __restrict__ part) {
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_split, r1 = min(R, r0 + rows_per_split);
+  if (VEC) {
+    const int64_t c = ((int64_t)blockIdx.x * ERIT_THREADS + threadIdx.x) * 2;
+    if (c >= C) return;
+    double2 acc = make_double2(0.0, 0.0);
+    int64_t r = r0;
+    for (; r + 4 <= r1; r += 4) {
+      double2 e[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) e[q] = __ldcs(reinterpret_cast<const double2*>(eri + (r + q) * C + c));
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const double j = __ldg(Jbar + r + q); acc.x = fma(j, e[q].x, acc.x); acc.y = fma(j, e[q].y, acc.y); }
+    }
+    for (; r < r1; r++) {
+      const double2 e = __ldcs(reinterpret_cast<const double2*>(eri + r * C + c));
+      const double j = __ldg(Jbar + r);
+      acc.x = fma(j, e.x, acc.x); acc.y = fma(j, e.y, acc.y);
+    }
+    *reinterpret_cast<double2*>(part + (int64_t)blockIdx.y * C + c) = acc;
+  } else {
+    const int64_t c = (int64_t)blockIdx.x * ERIT_THREADS + threadIdx.x;
+    if (c >= C) return;
+    double acc = 0.0;
+    for (int64_t r = r0; r < r1; r++) acc = fma(__ldg(Jbar + r), __ldcs(eri + r * C + c), acc);
+    part[(int64_t)blockIdx.y * C + c] = acc;
+  }
+}
+
+__global__ void sum_splits_kernel(int64_t C, int splits, const double* __restrict__ part, double* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int s = 0; s < splits; s++) acc += part[(int64_t)s * C + c];
+  out[c] = acc;
+}
+
+// out[0] = scale * sum_i a[i] b[i]   (single CTA, fixed order)
+__global__ void __launch_bounds__(1024) dot_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                                  double scale, double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc = fma(a[i], b[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = red[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = scale * v;
+  }
+}
+
+// K[p][r] += sum_t eri[p][q][r][t] P[q][t]  for all q: one CTA per (p, r-block); not in the reference
+//  -- same ERI stream with the other index pairing.
+__global__ void __launch_bounds__(256) eri_k_kernel(int n, const double* __restrict__ eri, const double* __restrict__ P,
+                                                   double* __restrict__ K) {
+  // warp w of the CTA handles r = blockIdx.y*8 + w; loops over q; lanes stride t
+  const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.y * 8 + warp;
+  if (r >= n) return;
+  double acc = 0.0;
+  for (int q = 0; q < n; q++) {
+    const double* e = eri + (((size_t)p * n + q) * n + r) * n;
+    const double* pq = P + (size_t)q * n;
+    for (int t = lane; t < n; t += 32) acc = fma(__ldcs(e + t), __ldg(pq + t), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) K[(size_t)p * n + r] = acc;
+}
+
+size_t eri_workspace(int64_t n) {
+  if (n <= 0) return 0;
+  const int64_t C = n * n;
+  return (size_t)64 * C * 8 + 512;  // row-split partials of the transposed sweep
+}
+
+// ---------------------------------------------------------------------------------------------------
+// XC quadrature                                       grad_dft/functional.py:251-253, 342; molecule.py:687-689
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double aclip(double x, double c) { return fabs(x) > c ? x : 0.0; }
+
+constexpr int INT_THREADS = 256;
+constexpr int INT_MAX_BLOCKS = 1184;  // 8 x 148
+
+__global__ void __launch_bounds__(INT_THREADS) integrate_fwd_kernel(int64_t N, int F, int64_t c_rows, const double* __restrict__ c,
+                                                                   const double* __restrict__ d, const double* __restrict__ w,
+                                                                   double clip, double* __restrict__ partial) {
+  __shared__ double red[INT_THREADS / 32];
+  double acc = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * INT_THREADS + threadIdx.x; r < N; r += (int64_t)gridDim.x * INT_THREADS) {
+    const double* cr = c + (c_rows == 1 ? 0 : r * F);
+    const double* dr = d + r * F;
+    double e = 0.0;
+    for (int f = 0; f < F; f++) e = fma(cr[f], dr[f], e);
+    e = aclip(aclip(e, clip), clip);
+    acc = fma(aclip(w[r], clip), e, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < INT_THREADS / 32; i++) s += red[i];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) sum_partials_kernel(int count, int stride, int ncol, const double* __restrict__ partial,
+                                                           double* __restrict__ out) {
+  // out[col] = sum_i partial[i*stride + col]; one CTA, fixed order
+  __shared__ double red[32];
+  for (int col = 0; col < ncol; col++) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < count; i += 1024) acc += partial[(size_t)i * stride + col];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double v = red[threadIdx.x];
+      v = warp_sum(v);
+      if (threadIdx.x == 0) out[col] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// e_bar_r = E_bar * aclip(w_r) * [|e_r| > clip];  d_bar[r,f] = e_bar_r c[r,f];  c_bar[r,f] = e_bar_r d[r,f]
+// (c_rows == 1: c_bar[f] = sum_r e_bar_r d[r,f] via per-block partials)
+__global__ void __launch_bounds__(INT_THREADS) integrate_bwd_kernel(int64_t N, int F, int64_t c_rows, const double* __restrict__ c,
+                                                                   const double* __restrict__ d, const double* __restrict__ w,
+                                                                   double clip, const double* __restrict__ E_bar,
+                                                                   double* __restrict__ c_bar, double* __restrict__ d_bar,
+                                                                   double* __restrict__ partial /*[grid][F] when c_rows==1 && c_bar*/) {
+  __shared__ double red[INT_THREADS / 32];
+  const double Eb = E_bar[0];
+  double cacc[32];
+  const bool reduce_c = (c_rows == 1) && (c_bar != nullptr);
+  if (reduce_c)
+    for (int f = 0; f < F; f++) cacc[f] = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * INT_THREADS + threadIdx.x; r < N; r += (int64_t)gridDim.x * INT_THREADS) {
+    const double* cr = c + (c_rows == 1 ? 0 : r * F);
+    const double* dr = d + r * F;
+    double e = 0.0;
+    for (int f = 0; f < F; f++) e = fma(cr[f], dr[f], e);
+    const double eb = (fabs(e) > clip) ? Eb * aclip(w[r], clip) : 0.0;
+    if (d_bar)
+      for (int f = 0; f < F; f++) d_bar[r * F + f] = eb * cr[f];
+    if (c_bar) {
+      if (reduce_c) {
+        for (int f = 0; f < F; f++) cacc[f] = fma(eb, dr[f], cacc[f]);
+      } else {
+        for (int f = 0; f < F; f++) c_bar[r * F + f] = eb * dr[f];
+      }
+    }
+  }
+  if (reduce_c) {
+    for (int f = 0; f < F; f++) {
+      double v = warp_sum(cacc[f]);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < INT_THREADS / 32; i++) s += red[i];
+        partial[(size_t)blockIdx.x * F + f] = s;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+size_t integrate_workspace(int64_t) { return (size_t)INT_MAX_BLOCKS * 32 * 8 + 512; }
+
+// ---------------------------------------------------------------------------------------------------
+// predictor glue                                                        grad_dft/train.py:148-163, 205-215
+// ---------------------------------------------------------------------------------------------------
+__global__ void fock_assemble_kernel(int n, const double* __restrict__ h1e, const double* __restrict__ J,
+                                     const double* __restrict__ Dbar, double clip, double* __restrict__ fock) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * n * n) return;
+  const int s = idx / (n * n), rem = idx - s * n * n, i = rem / n, j = rem - i * n;
+  const int ij = i * n + j, ji = j * n + i;
+  const double x = aclip(h1e[ij] + J[ij] + Dbar[s * n * n + ij], clip);
+  const double xt = aclip(h1e[ji] + J[ji] + Dbar[s * n * n + ji], clip);
+  fock[idx] = aclip(0.5 * (x + xt), clip);
+}
+__global__ void fock_add_sym_kernel(int n, const double* __restrict__ V, double clip, double* __restrict__ fock) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * n * n) return;
+  const int s = idx / (n * n), rem = idx - s * n * n, i = rem / n, j = rem - i * n;
+  fock[idx] = aclip(fock[idx] + (V[idx] + V[s * n * n + j * n + i]), clip);
+}
+
+}  // namespace gdft
+
+using namespace gdft;
+
+extern "C" int gdft_eri_jk(gdft_stream_t stream_, int64_t n, const double* eri, const double* P, double* J, double* K,
+                           double* EJ, void* ws, size_t ws_bytes) {
+  (void)ws; (void)ws_bytes;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || n > 2048) return GDFT_BAD_SHAPE;
+  if (!eri || !P || !J) return GDFT_BAD_ARGUMENT;
+  const int64_t R = n * n, C = n * n;
+  const bool vec = (C % 2 == 0) && aligned16(eri);
+  const int64_t nblocks = (R + ERI_ROWS_PER_CTA - 1) / ERI_ROWS_PER_CTA;
+  const unsigned grid = (unsigned)imin64(nblocks, 148 * 8);
+  if (vec) eri_j_kernel<true><<<grid, ERI_THREADS, 0, stream>>>(R, C, eri, P, J);
+  else eri_j_kernel<false><<<grid, ERI_THREADS, 0, stream>>>(R, C, eri, P, J);
+  GDFT_LAUNCH_CHECK();
+  if (K) {
+    dim3 g((unsigned)n, (unsigned)((n + 7) / 8));
+    eri_k_kernel<<<g, 256, 0, stream>>>((int)n, eri, P, K);
+    GDFT_LAUNCH_CHECK();
+  }
+  if (EJ) {
+    dot_kernel<<<1, 1024, 0, stream>>>(R, P, J, 0.5, EJ);
+    GDFT_LAUNCH_CHECK();
+  }
+  return GDFT_OK;
+}
+
+extern "C" int gdft_eri_j_transpose(gdft_stream_t stream_, int64_t n, const double* eri, const double* Jbar, double* Pbar,
+                                    void* ws, size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || n > 2048) return GDFT_BAD_SHAPE;
+  if (!eri || !Jbar || !Pbar) return GDFT_BAD_ARGUMENT;
+  if (!aligned16(ws)) return GDFT_BAD_ALIGNMENT;
+  if (ws_bytes < eri_workspace(n)) return GDFT_WORKSPACE_TOO_SMALL;
+  const int64_t R = n * n, C = n * n;
+  const bool vec = (C % 2 == 0) && aligned16(eri);
+  int splits = (int)imin64(64, imax64(1, R / 64));
+  const int64_t rows_per_split = (R + splits - 1) / splits;
+  double* part = static_cast<double*>(ws);
+  const int64_t cols_per_cta = vec ? 2 * ERIT_THREADS : ERIT_THREADS;
+  dim3 grid((unsigned)((C + cols_per_cta - 1) / cols_per_cta), (unsigned)splits);
+  if (vec) eri_jt_kernel<true><<<grid, ERIT_THREADS, 0, stream>>>(R, C, rows_per_split, eri, Jbar, part);
+  else eri_jt_kernel<false><<<grid, ERIT_THREADS, 0, stream>>>(R, C, rows_per_split, eri, Jbar, part);
+  GDFT_LAUNCH_CHECK();
+  sum_splits_kernel<<<(unsigned)((C + 255) / 256), 256, 0, stream>>>(C, splits, part, Pbar);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+extern "C" int gdft_xc_integrate_fwd(gdft_stream_t stream_, int64_t N, int F, int64_t c_rows, const double* c, const double* d,
+                                     const double* w, double clip, double* E, void* ws, size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N <= 0 || F <= 0 || F > 32 || (c_rows != 1 && c_rows != N)) return GDFT_BAD_SHAPE;
+  if (!c || !d || !w || !E) return GDFT_BAD_ARGUMENT;
+  if (ws_bytes < integrate_workspace(N)) return GDFT_WORKSPACE_TOO_SMALL;
+  const int grid = (int)imin64(INT_MAX_BLOCKS, (N + INT_THREADS - 1) / INT_THREADS);
+  double* partial = static_cast<double*>(ws);
+  integrate_fwd_kernel<<<grid, INT_THREADS, 0, stream>>>(N, F, c_rows, c, d, w, clip, partial);
+  GDFT_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, 1024, 0, stream>>>(grid, 1, 1, partial, E);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+extern "C" int gdft_xc_integrate_bwd(gdft_stream_t stream_, int64_t N, int F, int64_t c_rows, const double* c, const double* d,
+                                     const double* w, double clip, const double* E_bar, double* c_bar, double* d_bar, void* ws,
+                                     size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N <= 0 || F <= 0 || F > 32 || (c_rows != 1 && c_rows != N)) return GDFT_BAD_SHAPE;
+  if (!c || !d || !w || !E_bar) return GDFT_BAD_ARGUMENT;
+  if (ws_bytes < integrate_workspace(N)) return GDFT_WORKSPACE_TOO_SMALL;
+  const int grid = (int)imin64(INT_MAX_BLOCKS, (N + INT_THREADS - 1) / INT_THREADS);
+  double* partial = static_cast<double*>(ws);
+  integrate_bwd_kernel<<<grid, INT_THREADS, 0, stream>>>(N, F, c_rows, c, d, w, clip, E_bar, c_bar, d_bar, partial);
+  GDFT_LAUNCH_CHECK();
+  if (c_bar && c_rows == 1) {
+    sum_partials_kernel<<<1, 1024, 0, stream>>>(grid, F, F, partial, c_bar);
+    GDFT_LAUNCH_CHECK();
+  }
+  return GDFT_OK;
+}
+
+extern "C" int gdft_fock_assemble(gdft_stream_t stream, int64_t n, const double* h1e, const double* J, const double* rdm1_bar,
+                                  double clip, double* fock) {
+  if (n <= 0 || n > 32768) return GDFT_BAD_SHAPE;
+  if (!h1e || !J || !rdm1_bar || !fock) return GDFT_BAD_ARGUMENT;
+  const int total = (int)(2 * n * n);
+  fock_assemble_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>((int)n, h1e, J, rdm1_bar, clip, fock);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+extern "C" int gdft_fock_add_sym(gdft_stream_t stream, int64_t n, const double* V, double clip, double* fock) {
+  if (n <= 0 || n > 32768) return GDFT_BAD_SHAPE;
+  if (!V || !fock) return GDFT_BAD_ARGUMENT;
+  const int total = (int)(2 * n * n);
+  fock_add_sym_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>((int)n, V, clip, fock);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}

@@ -1,0 +1,233 @@
+// K5 -- closed-form per-point features, forward and reverse (one thread per grid point; HBM-streaming).
+// The reverse pass evaluates the same template code on forward-mode dual numbers over the six local
+// variables (rho_a, rho_b, sigma_aa, sigma_bb, x_a, x_b) with x = laplacian (LYP) or tau (DM21 MGGA),
+// contracts with the output cotangent and applies d sigma_ss / d grad_rho_s = 2 grad_rho_s.
+#include "common.cuh"
+#include "pointwise_math.h"
+
+namespace gdft {
+
+using pw::Dual;
+
+__host__ __device__ inline int pointwise_ncols(int id) {
+  switch (id) {
+    case GDFT_PW_LSDA_X: case GDFT_PW_B88_X: case GDFT_PW_VWN_C: case GDFT_PW_LYP_C: case GDFT_PW_PW92_C: case GDFT_PW_DM21_LDA: return 1;
+    case GDFT_PW_B88_SET: case GDFT_PW_DM21_GGA: return 2;
+    case GDFT_PW_B3LYP_SET: case GDFT_PW_DM21_MGGA: return 4;
+    case GDFT_PW_DM21_INPUTS: return 7;
+    default: return 0;
+  }
+}
+// bit 0: grad_rho, bit 1: lapl, bit 2: tau
+__host__ __device__ inline int pointwise_needs(int id) {
+  switch (id) {
+    case GDFT_PW_B88_X: case GDFT_PW_B88_SET: case GDFT_PW_DM21_GGA: return 1;
+    case GDFT_PW_LYP_C: case GDFT_PW_B3LYP_SET: return 1 | 2;
+    case GDFT_PW_DM21_MGGA: return 1 | 4;
+    case GDFT_PW_DM21_INPUTS: return 1 | 4;
+    default: return 0;
+  }
+}
+
+// feats[] for every id except DM21_INPUTS; v = {ra, rb, saa, sbb, xa, xb}
+template <int ID, typename T>
+__device__ __forceinline__ void eval_features(const T (&v)[6], double clip, T* feats) {
+  if (ID == GDFT_PW_LSDA_X) feats[0] = pw::lsda_x(v[0], v[1], clip);
+  if (ID == GDFT_PW_B88_X) feats[0] = pw::b88_x(v[0], v[1], v[2], v[3], clip);
+  if (ID == GDFT_PW_VWN_C) feats[0] = pw::vwn_c(v[0], v[1], clip);
+  if (ID == GDFT_PW_LYP_C) feats[0] = pw::lyp_c(v[0], v[1], v[2], v[3], v[4], v[5], clip);
+  if (ID == GDFT_PW_PW92_C) feats[0] = pw::pw92_c(v[0], v[1], clip);
+  if (ID == GDFT_PW_B88_SET) {
+    feats[0] = pw::lsda_x(v[0], v[1], clip);
+    feats[1] = pw::b88_x(v[0], v[1], v[2], v[3], clip);
+  }
+  if (ID == GDFT_PW_B3LYP_SET) {
+    feats[0] = pw::lsda_x(v[0], v[1], clip);
+    feats[1] = pw::b88_x(v[0], v[1], v[2], v[3], clip);
+    feats[2] = pw::vwn_c(v[0], v[1], clip);
+    feats[3] = pw::lyp_c(v[0], v[1], v[2], v[3], v[4], v[5], clip);
+  }
+  if (ID == GDFT_PW_DM21_LDA || ID == GDFT_PW_DM21_GGA || ID == GDFT_PW_DM21_MGGA) {
+    const int nu = (ID == GDFT_PW_DM21_LDA) ? 1 : 2, nw = (ID == GDFT_PW_DM21_MGGA) ? 2 : 1;
+    int col = 0;
+    for (int i = 0; i < nu; i++)
+      for (int j = 0; j < nw; j++) {
+        T term = pw::dm21_term_spin(v[0], v[2], v[4], i, j, clip) + pw::dm21_term_spin(v[1], v[3], v[5], i, j, clip);
+        if (i == 0 && j == 0) term = term * (-2.0 * pw::PI * pow(3.0 / (4.0 * pw::PI), 4.0 / 3.0));
+        feats[col++] = term;
+      }
+  }
+}
+
+struct PwArgs {
+  int64_t N;
+  double clip;
+  const double *rho, *grho, *tau, *lapl, *out_bar;
+  double *out, *rho_bar, *grho_bar, *tau_bar, *lapl_bar;
+};
+
+template <int ID>
+__global__ void __launch_bounds__(128) pointwise_fwd_kernel(const PwArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.N) return;
+  constexpr int F = (ID == GDFT_PW_B88_SET || ID == GDFT_PW_DM21_GGA) ? 2 : (ID == GDFT_PW_B3LYP_SET || ID == GDFT_PW_DM21_MGGA) ? 4 : 1;
+  const int needs = pointwise_needs(ID);
+  const double2 rho = reinterpret_cast<const double2*>(a.rho)[r];
+  double v[6] = {rho.x, rho.y, 0, 0, 0, 0};
+  if (needs & 1) {
+    const double* g = a.grho + r * 6;
+    v[2] = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+    v[3] = g[3] * g[3] + g[4] * g[4] + g[5] * g[5];
+  }
+  if (needs & 2) { const double2 l = reinterpret_cast<const double2*>(a.lapl)[r]; v[4] = l.x; v[5] = l.y; }
+  if (needs & 4) { const double2 l = reinterpret_cast<const double2*>(a.tau)[r]; v[4] = l.x; v[5] = l.y; }
+  double feats[F];
+  eval_features<ID, double>(v, a.clip, feats);
+#pragma unroll
+  for (int f = 0; f < F; f++) a.out[r * F + f] = feats[f];
+}
+
+template <int ID>
+__global__ void __launch_bounds__(128) pointwise_bwd_kernel(const PwArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.N) return;
+  constexpr int F = (ID == GDFT_PW_B88_SET || ID == GDFT_PW_DM21_GGA) ? 2 : (ID == GDFT_PW_B3LYP_SET || ID == GDFT_PW_DM21_MGGA) ? 4 : 1;
+  const int needs = pointwise_needs(ID);
+  typedef Dual<6> D6;
+  const double2 rho = reinterpret_cast<const double2*>(a.rho)[r];
+  double g[6] = {0, 0, 0, 0, 0, 0};
+  double x[6] = {rho.x, rho.y, 0, 0, 0, 0};
+  if (needs & 1) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) g[q] = a.grho[r * 6 + q];
+    x[2] = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+    x[3] = g[3] * g[3] + g[4] * g[4] + g[5] * g[5];
+  }
+  if (needs & 2) { const double2 l = reinterpret_cast<const double2*>(a.lapl)[r]; x[4] = l.x; x[5] = l.y; }
+  if (needs & 4) { const double2 l = reinterpret_cast<const double2*>(a.tau)[r]; x[4] = l.x; x[5] = l.y; }
+  D6 v[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) v[q] = pw::Make<D6>::variable(x[q], q);
+  D6 feats[F];
+  eval_features<ID, D6>(v, a.clip, feats);
+  double d[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int f = 0; f < F; f++) {
+    const double ob = a.out_bar[r * F + f];
+#pragma unroll
+    for (int q = 0; q < 6; q++) d[q] = fma(ob, feats[f].d[q], d[q]);
+  }
+  if (a.rho_bar) reinterpret_cast<double2*>(a.rho_bar)[r] = make_double2(d[0], d[1]);
+  if (a.grho_bar) {
+    double* o = a.grho_bar + r * 6;
+#pragma unroll
+    for (int j = 0; j < 3; j++) { o[j] = 2.0 * d[2] * g[j]; o[3 + j] = 2.0 * d[3] * g[3 + j]; }
+  }
+  if (a.lapl_bar) reinterpret_cast<double2*>(a.lapl_bar)[r] = (needs & 2) ? make_double2(d[4], d[5]) : make_double2(0.0, 0.0);
+  if (a.tau_bar) reinterpret_cast<double2*>(a.tau_bar)[r] = (needs & 4) ? make_double2(d[4], d[5]) : make_double2(0.0, 0.0);
+}
+
+// functional.py:520-531: [rho'_a, rho'_b, |g_a+g_b|^2, |g_a|^2, |g_b|^2, tau_a, tau_b], rho' = max(|rho|,clip) sign(rho)
+__global__ void __launch_bounds__(128) dm21_inputs_fwd_kernel(const PwArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.N) return;
+  const double2 rho = reinterpret_cast<const double2*>(a.rho)[r];
+  const double2 tau = reinterpret_cast<const double2*>(a.tau)[r];
+  const double* g = a.grho + r * 6;
+  auto squash = [&](double x) { const double s = (x > 0.0) - (x < 0.0); return fmax(fabs(x), a.clip) * s; };
+  double* o = a.out + r * 7;
+  o[0] = squash(rho.x); o[1] = squash(rho.y);
+  double st = 0, sa = 0, sb = 0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) { const double t = g[j] + g[3 + j]; st += t * t; sa += g[j] * g[j]; sb += g[3 + j] * g[3 + j]; }
+  o[2] = st; o[3] = sa; o[4] = sb; o[5] = tau.x; o[6] = tau.y;
+}
+__global__ void __launch_bounds__(128) dm21_inputs_bwd_kernel(const PwArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.N) return;
+  const double2 rho = reinterpret_cast<const double2*>(a.rho)[r];
+  const double* g = a.grho + r * 6;
+  const double* ob = a.out_bar + r * 7;
+  // d/dx [max(|x|,c) sign(x)] = 1 where |x| > c (ties follow torch.maximum: 1/2), else 0
+  auto dsq = [&](double x) { const double ax = fabs(x); return ax > a.clip ? 1.0 : (ax == a.clip ? 0.5 : 0.0); };
+  if (a.rho_bar) reinterpret_cast<double2*>(a.rho_bar)[r] = make_double2(ob[0] * dsq(rho.x), ob[1] * dsq(rho.y));
+  if (a.grho_bar) {
+    double* o = a.grho_bar + r * 6;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double t = 2.0 * (g[j] + g[3 + j]) * ob[2];
+      o[j] = t + 2.0 * g[j] * ob[3];
+      o[3 + j] = t + 2.0 * g[3 + j] * ob[4];
+    }
+  }
+  if (a.tau_bar) reinterpret_cast<double2*>(a.tau_bar)[r] = make_double2(ob[5], ob[6]);
+  if (a.lapl_bar) reinterpret_cast<double2*>(a.lapl_bar)[r] = make_double2(0.0, 0.0);
+}
+
+template <int ID>
+static void launch_pw(bool bwd, cudaStream_t st, const PwArgs& a) {
+  const unsigned grid = (unsigned)((a.N + 127) / 128);
+  if (bwd) pointwise_bwd_kernel<ID><<<grid, 128, 0, st>>>(a);
+  else pointwise_fwd_kernel<ID><<<grid, 128, 0, st>>>(a);
+}
+
+static int dispatch_pw(bool bwd, cudaStream_t st, int id, const PwArgs& a) {
+  const unsigned grid = (unsigned)((a.N + 127) / 128);
+  switch (id) {
+    case GDFT_PW_LSDA_X: launch_pw<GDFT_PW_LSDA_X>(bwd, st, a); break;
+    case GDFT_PW_B88_X: launch_pw<GDFT_PW_B88_X>(bwd, st, a); break;
+    case GDFT_PW_VWN_C: launch_pw<GDFT_PW_VWN_C>(bwd, st, a); break;
+    case GDFT_PW_LYP_C: launch_pw<GDFT_PW_LYP_C>(bwd, st, a); break;
+    case GDFT_PW_PW92_C: launch_pw<GDFT_PW_PW92_C>(bwd, st, a); break;
+    case GDFT_PW_B3LYP_SET: launch_pw<GDFT_PW_B3LYP_SET>(bwd, st, a); break;
+    case GDFT_PW_B88_SET: launch_pw<GDFT_PW_B88_SET>(bwd, st, a); break;
+    case GDFT_PW_DM21_LDA: launch_pw<GDFT_PW_DM21_LDA>(bwd, st, a); break;
+    case GDFT_PW_DM21_GGA: launch_pw<GDFT_PW_DM21_GGA>(bwd, st, a); break;
+    case GDFT_PW_DM21_MGGA: launch_pw<GDFT_PW_DM21_MGGA>(bwd, st, a); break;
+    case GDFT_PW_DM21_INPUTS:
+      if (bwd) dm21_inputs_bwd_kernel<<<grid, 128, 0, st>>>(a);
+      else dm21_inputs_fwd_kernel<<<grid, 128, 0, st>>>(a);
+      break;
+    default: return GDFT_BAD_ARGUMENT;
+  }
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+static int check_pw_inputs(int64_t N, int id, const double* rho, const double* grho, const double* tau, const double* lapl) {
+  if (N <= 0) return GDFT_BAD_SHAPE;
+  if (id < 0 || id >= GDFT_PW_COUNT) return GDFT_BAD_ARGUMENT;
+  const int needs = pointwise_needs(id);
+  if (!rho || ((needs & 1) && !grho) || ((needs & 2) && !lapl) || ((needs & 4) && !tau)) return GDFT_BAD_ARGUMENT;
+  if (!aligned16(rho) || !aligned16(tau) || !aligned16(lapl)) return GDFT_BAD_ALIGNMENT;
+  return GDFT_OK;
+}
+
+}  // namespace gdft
+
+using namespace gdft;
+
+extern "C" int gdft_pointwise_ncols(int id) { return pointwise_ncols(id); }
+
+extern "C" int gdft_pointwise_fwd(gdft_stream_t stream, int64_t N, int id, double clip, const double* rho, const double* grad_rho,
+                                  const double* tau, const double* lapl, double* out) {
+  int rc = check_pw_inputs(N, id, rho, grad_rho, tau, lapl);
+  if (rc) return rc;
+  if (!out) return GDFT_BAD_ARGUMENT;
+  PwArgs a{};
+  a.N = N; a.clip = clip; a.rho = rho; a.grho = grad_rho; a.tau = tau; a.lapl = lapl; a.out = out;
+  return dispatch_pw(false, static_cast<cudaStream_t>(stream), id, a);
+}
+
+extern "C" int gdft_pointwise_bwd(gdft_stream_t stream, int64_t N, int id, double clip, const double* rho, const double* grad_rho,
+                                  const double* tau, const double* lapl, const double* out_bar, double* rho_bar,
+                                  double* grad_rho_bar, double* tau_bar, double* lapl_bar) {
+  int rc = check_pw_inputs(N, id, rho, grad_rho, tau, lapl);
+  if (rc) return rc;
+  if (!out_bar) return GDFT_BAD_ARGUMENT;
+  if (!aligned16(rho_bar) || !aligned16(tau_bar) || !aligned16(lapl_bar)) return GDFT_BAD_ALIGNMENT;
+  PwArgs a{};
+  a.N = N; a.clip = clip; a.rho = rho; a.grho = grad_rho; a.tau = tau; a.lapl = lapl; a.out_bar = out_bar;
+  a.rho_bar = rho_bar; a.grho_bar = grad_rho_bar; a.tau_bar = tau_bar; a.lapl_bar = lapl_bar;
+  return dispatch_pw(true, static_cast<cudaStream_t>(stream), id, a);
+}

@@ -1,0 +1,279 @@
+// Closed-form per-grid-point functionals of Grad DFT, written once as scalar-type-generic templates:
+// T = double gives values, T = Dual<NV> (forward-mode dual numbers) gives values + exact first
+// derivatives with the reference's jnp.clip / jnp.where sub-gradient conventions
+// (clip: zero derivative where clipped; where: derivative of the selected branch only).
+// Compiles as CUDA device code (pointwise.cu) and as plain host C++ (tests/native, CPU unit tests of
+// the formulas against the oracle -- the product only ever runs the device build).
+//
+// Formulas follow, line by line:
+//   grad_dft/functional.py:950-979   exchange_polarization_correction
+//   grad_dft/functional.py:982-1045  correlation_polarization_correction
+//   grad_dft/popular_functionals.py:29-50 lsda_x_e, 52-103 b88_x_e, 105-139 pw92_c_e,
+//                                   141-195 vwn_c_e, 197-269 lyp_c_e
+//   grad_dft/functional.py:504-531   dm21_coefficient_inputs, 534-626 dm21_densities
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define GDFT_HD __host__ __device__ __forceinline__
+#else
+#define GDFT_HD inline
+#endif
+
+namespace gdft {
+namespace pw {
+
+constexpr double LN2 = 0.693147180559945309417232121458;
+constexpr double PI = 3.14159265358979323846264338328;
+
+template <int NV>
+struct Dual {
+  double v;
+  double d[NV];
+};
+
+// ---- construction ---------------------------------------------------------------------------------
+template <typename T> struct Make;
+template <> struct Make<double> {
+  static GDFT_HD double constant(double c) { return c; }
+  static GDFT_HD double variable(double x, int) { return x; }
+};
+template <int NV> struct Make<Dual<NV>> {
+  static GDFT_HD Dual<NV> constant(double c) {
+    Dual<NV> r; r.v = c;
+#pragma unroll
+    for (int i = 0; i < NV; i++) r.d[i] = 0.0;
+    return r;
+  }
+  static GDFT_HD Dual<NV> variable(double x, int idx) {
+    Dual<NV> r; r.v = x;
+#pragma unroll
+    for (int i = 0; i < NV; i++) r.d[i] = (i == idx) ? 1.0 : 0.0;
+    return r;
+  }
+};
+
+GDFT_HD double val(double x) { return x; }
+template <int NV> GDFT_HD double val(const Dual<NV>& x) { return x.v; }
+
+// chain rule helper: f(x) with value fv and derivative fd
+template <int NV> GDFT_HD Dual<NV> chain(const Dual<NV>& x, double fv, double fd) {
+  Dual<NV> r; r.v = fv;
+#pragma unroll
+  for (int i = 0; i < NV; i++) r.d[i] = fd * x.d[i];
+  return r;
+}
+
+// ---- arithmetic -----------------------------------------------------------------------------------
+template <int NV> GDFT_HD Dual<NV> operator+(const Dual<NV>& a, const Dual<NV>& b) {
+  Dual<NV> r; r.v = a.v + b.v;
+#pragma unroll
+  for (int i = 0; i < NV; i++) r.d[i] = a.d[i] + b.d[i];
+  return r;
+}
+template <int NV> GDFT_HD Dual<NV> operator-(const Dual<NV>& a, const Dual<NV>& b) {
+  Dual<NV> r; r.v = a.v - b.v;
+#pragma unroll
+  for (int i = 0; i < NV; i++) r.d[i] = a.d[i] - b.d[i];
+  return r;
+}
+template <int NV> GDFT_HD Dual<NV> operator*(const Dual<NV>& a, const Dual<NV>& b) {
+  Dual<NV> r; r.v = a.v * b.v;
+#pragma unroll
+  for (int i = 0; i < NV; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+  return r;
+}
+template <int NV> GDFT_HD Dual<NV> operator/(const Dual<NV>& a, const Dual<NV>& b) {
+  Dual<NV> r; r.v = a.v / b.v;
+  const double inv = 1.0 / b.v;
+#pragma unroll
+  for (int i = 0; i < NV; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
+  return r;
+}
+template <int NV> GDFT_HD Dual<NV> operator-(const Dual<NV>& a) {
+  Dual<NV> r; r.v = -a.v;
+#pragma unroll
+  for (int i = 0; i < NV; i++) r.d[i] = -a.d[i];
+  return r;
+}
+template <int NV> GDFT_HD Dual<NV> operator+(const Dual<NV>& a, double c) { Dual<NV> r = a; r.v += c; return r; }
+template <int NV> GDFT_HD Dual<NV> operator+(double c, const Dual<NV>& a) { return a + c; }
+template <int NV> GDFT_HD Dual<NV> operator-(const Dual<NV>& a, double c) { Dual<NV> r = a; r.v -= c; return r; }
+template <int NV> GDFT_HD Dual<NV> operator-(double c, const Dual<NV>& a) { return (-a) + c; }
+template <int NV> GDFT_HD Dual<NV> operator*(const Dual<NV>& a, double c) {
+  Dual<NV> r; r.v = a.v * c;
+#pragma unroll
+  for (int i = 0; i < NV; i++) r.d[i] = a.d[i] * c;
+  return r;
+}
+template <int NV> GDFT_HD Dual<NV> operator*(double c, const Dual<NV>& a) { return a * c; }
+template <int NV> GDFT_HD Dual<NV> operator/(const Dual<NV>& a, double c) { return a * (1.0 / c); }
+template <int NV> GDFT_HD Dual<NV> operator/(double c, const Dual<NV>& a) { return chain(a, c / a.v, -c / (a.v * a.v)); }
+
+// ---- elementary functions (double overloads first) --------------------------------------------------
+GDFT_HD double f_log2(double x) { return log2(x); }
+GDFT_HD double f_exp2(double x) { return exp2(x); }
+GDFT_HD double f_log(double x) { return log(x); }
+GDFT_HD double f_exp(double x) { return exp(x); }
+GDFT_HD double f_sqrt(double x) { return sqrt(x); }
+GDFT_HD double f_atan(double x) { return atan(x); }
+GDFT_HD double f_asinh(double x) { return asinh(x); }
+GDFT_HD double f_pow(double x, double p) { return pow(x, p); }
+GDFT_HD double f_clip_min(double x, double c) { return x >= c ? x : c; }
+GDFT_HD double f_select(bool cond, double a, double b) { return cond ? a : b; }
+
+template <int NV> GDFT_HD Dual<NV> f_log2(const Dual<NV>& x) { return chain(x, log2(x.v), 1.0 / (x.v * LN2)); }
+template <int NV> GDFT_HD Dual<NV> f_exp2(const Dual<NV>& x) { const double e = exp2(x.v); return chain(x, e, e * LN2); }
+template <int NV> GDFT_HD Dual<NV> f_log(const Dual<NV>& x) { return chain(x, log(x.v), 1.0 / x.v); }
+template <int NV> GDFT_HD Dual<NV> f_exp(const Dual<NV>& x) { const double e = exp(x.v); return chain(x, e, e); }
+template <int NV> GDFT_HD Dual<NV> f_sqrt(const Dual<NV>& x) { const double s = sqrt(x.v); return chain(x, s, 0.5 / s); }
+template <int NV> GDFT_HD Dual<NV> f_atan(const Dual<NV>& x) { return chain(x, atan(x.v), 1.0 / (1.0 + x.v * x.v)); }
+template <int NV> GDFT_HD Dual<NV> f_asinh(const Dual<NV>& x) { return chain(x, asinh(x.v), 1.0 / sqrt(1.0 + x.v * x.v)); }
+template <int NV> GDFT_HD Dual<NV> f_pow(const Dual<NV>& x, double p) { return chain(x, pow(x.v, p), p * pow(x.v, p - 1.0)); }
+// jnp.clip(x, a_min=c): value max(x,c); derivative passes where x >= c (torch.clamp convention at the tie)
+template <int NV> GDFT_HD Dual<NV> f_clip_min(const Dual<NV>& x, double c) { return x.v >= c ? x : Make<Dual<NV>>::constant(c); }
+template <int NV> GDFT_HD Dual<NV> f_select(bool cond, const Dual<NV>& a, const Dual<NV>& b) { return cond ? a : b; }
+
+template <typename T> GDFT_HD T cst(double c) { return Make<T>::constant(c); }
+
+// ---- spin interpolation -------------------------------------------------------------------------------
+constexpr double FZ_DEN = 0.51984209978974632953442121455650;  // 2 (2^{1/3} - 1)
+constexpr double FZ_PP0 = 1.70992093416136561756560043006;     // f''(0) = 8 / (9 * FZ_DEN)
+constexpr double LOG2_RS0 = -0.68904830706500979;              // log2((3/(4 pi))^{1/3})
+
+// functional.py:973-979
+template <typename T> GDFT_HD T exchange_polarization(const T& eP, const T& eF, const T& ra, const T& rb) {
+  const T zeta = (ra - rb) / (ra + rb);
+  const T fz = (f_pow(1.0 - zeta, 4.0 / 3.0) + f_pow(1.0 + zeta, 4.0 / 3.0) - 2.0) / FZ_DEN;
+  return eP + (eF - eP) * fz;
+}
+
+// The PW92 "G" function in the reference's exp2/log2 form: 2A(1+a1 rs) ln(1 + 1/(2A(b1 rs^1/2 + b2 rs + b3 rs^3/2 + b4 rs^2)))
+template <typename T> GDFT_HD T pw_G(const T& log_rs, double A, double a1, double b1, double b2, double b3, double b4) {
+  const T ars = f_exp2(log2(a1) + log_rs);
+  const T brs_1_2 = f_exp2(log2(b1) + log_rs / 2.0);
+  const T brs = f_exp2(log2(b2) + log_rs);
+  const T brs_3_2 = f_exp2(log2(b3) + 3.0 * log_rs / 2.0);
+  const T brs2 = f_exp2(log2(b4) + 2.0 * log_rs);
+  return 2.0 * A * (1.0 + ars) * f_log(1.0 + (1.0 / (2.0 * A)) / (brs_1_2 + brs + brs_3_2 + brs2));
+}
+
+// functional.py:1008-1045
+template <typename T> GDFT_HD T correlation_polarization(const T& eP, const T& eF, const T& ra, const T& rb, double clip) {
+  const T rt = ra + rb;
+  const T log_rho = f_log2(f_clip_min(rt, clip));
+  const T log_rs = LOG2_RS0 - log_rho / 3.0;
+  const T zeta = f_select(val(rt) > clip, (ra - rb) / rt, cst<T>(0.0));
+  const T alphac = pw_G(log_rs, 0.016887, 0.11125, 10.357, 3.6231, 0.88026, 0.49671);
+  const T zm = f_exp2(4.0 * f_log2(1.0 - zeta) / 3.0);
+  const T zp = f_exp2(4.0 * f_log2(1.0 + zeta) / 3.0);
+  const T fz = (zm + zp - 2.0) / FZ_DEN;
+  const T z2 = zeta * zeta;
+  const T z4 = z2 * z2;
+  return eP + alphac * (fz / FZ_PP0) * (1.0 - z4) + (eF - eP) * fz * z4;
+}
+
+// ---- energy densities ---------------------------------------------------------------------------------
+// popular_functionals.py:41-50
+template <typename T> GDFT_HD T lsda_x(const T& ra_in, const T& rb_in, double clip) {
+  const T ra = f_clip_min(ra_in, clip), rb = f_clip_min(rb_in, clip);
+  const T rt43 = f_pow(ra + rb, 4.0 / 3.0);
+  const double cP = -0.75 * cbrt(3.0 / PI), cF = -0.75 * cbrt(6.0 / PI);
+  return exchange_polarization(cP * rt43, cF * rt43, ra, rb);
+}
+
+// popular_functionals.py:70-97, one spin channel's contribution (positive; caller negates the sum)
+template <typename T> GDFT_HD T b88_x_spin(const T& r_in, const T& sigma, double clip) {
+  const double beta = 0.0042;
+  const T r = f_clip_min(r_in, clip);
+  const T log_rho = f_log2(f_clip_min(r, clip));
+  const T log_g = f_log2(f_clip_min(sigma, clip)) / 2.0;
+  const T log_x = log_g - (4.0 / 3.0) * log_rho;
+  const T x = f_exp2(log_x);
+  return beta * f_exp2(4.0 * log_rho / 3.0 + 2.0 * log_x - f_log2(1.0 + 6.0 * beta * x * f_asinh(x)));
+}
+template <typename T> GDFT_HD T b88_x(const T& ra, const T& rb, const T& saa, const T& sbb, double clip) {
+  return -(b88_x_spin(ra, saa, clip) + b88_x_spin(rb, sbb, clip));
+}
+
+// popular_functionals.py:120-139
+template <typename T> GDFT_HD T pw92_c(const T& ra, const T& rb, double clip) {
+  const T rt = ra + rb;
+  const T log_rho = f_log2(f_clip_min(rt, clip));
+  const T log_rs = LOG2_RS0 - log_rho / 3.0;
+  const T eP = -pw_G(log_rs, 0.031091, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294);
+  const T eF = -pw_G(log_rs, 0.015545, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517);
+  return correlation_polarization(eP, eF, ra, rb, clip) * rt;
+}
+
+template <typename T> GDFT_HD T vwn_ePF(const T& x, const T& log_x, double A, double b, double c, double x0) {
+  const T X = f_exp2(2.0 * log_x) + f_exp2(log_x + log2(b)) + c;
+  const double X0 = x0 * x0 + b * x0 + c;
+  const double Q = sqrt(4.0 * c - b * b);
+  const T at = f_atan(Q / (2.0 * x + b));
+  const T xm = x - x0;
+  return (A / 2.0) * (2.0 * f_log(x) - f_log(X) + (2.0 * b / Q) * at -
+                      (b * x0 / X0) * (f_log(xm * xm / X) + (2.0 * (2.0 * x0 + b) / Q) * at));
+}
+// popular_functionals.py:158-195
+template <typename T> GDFT_HD T vwn_c(const T& ra_in, const T& rb_in, double clip) {
+  const T ra = f_select(val(ra_in) > clip, ra_in, cst<T>(0.0));
+  const T rb = f_select(val(rb_in) > clip, rb_in, cst<T>(0.0));
+  const T rt = ra + rb;
+  const T log_rho = f_log2(f_clip_min(rt, clip));
+  const T log_rs = LOG2_RS0 - log_rho / 3.0;
+  const T log_x = log_rs / 2.0;
+  const T x = f_exp2(log_x);
+  const T eP = vwn_ePF(x, log_x, 0.0621814, 3.72744, 12.9352, -0.10498);
+  const T eF = vwn_ePF(x, log_x, 0.0621814 / 2, 7.06042, 18.0578, -0.325);
+  return correlation_polarization(eP, eF, ra, rb, clip) * rt;
+}
+
+// popular_functionals.py:229-269
+template <typename T>
+GDFT_HD T lyp_c(const T& ra_in, const T& rb_in, const T& saa, const T& sbb, const T& la, const T& lb, double clip) {
+  const double a = 0.04918, b = 0.132, c = 0.2533, d = 0.349;
+  const double CF = 0.3 * pow(3.0 * PI * PI, 2.0 / 3.0);
+  const T ra = f_clip_min(ra_in, clip), rb = f_clip_min(rb_in, clip);
+  const T zero = cst<T>(0.0);
+  const T ta = (f_select(val(ra) > clip, saa / ra, zero) - la) / 8.0;
+  const T tb = (f_select(val(rb) > clip, sbb / rb, zero) - lb) / 8.0;
+  const T rt = ra + rb;
+  const bool live = val(rt) > clip;
+  const T frac = f_select(live, (ra * ra + rb * rb) / (rt * rt), cst<T>(1.0));
+  const T gamma = 2.0 * (1.0 - frac);
+  const T rhos_ts = rt * (ta + tb);
+  const T rho_t = ra * ta + rb * tb;
+  const T rho_lap = ra * la + rb * lb;
+  const T rhom1_3 = f_pow(rt, -1.0 / 3.0);
+  const T rho8_3 = f_pow(ra, 8.0 / 3.0) + f_pow(rb, 8.0 / 3.0);
+  const T rhom5_3 = f_pow(rt, -5.0 / 3.0);
+  const T expf = f_select(val(rt) > 0.0, f_exp(-c * rhom1_3), zero);
+  const T par = pow(2.0, 2.0 / 3.0) * CF * rho8_3 - rhos_ts + rho_t / 9.0 + rho_lap / 18.0;
+  const T brk = f_select(live, 2.0 * b * rhom5_3 * par * expf, zero);
+  return -a * f_select(live, gamma / (1.0 + d * rhom1_3) * (rt + brk), zero);
+}
+
+// functional.py:594-623: one spin channel of the u^i w^j expansion, unscaled
+template <typename T> GDFT_HD T dm21_term_spin(const T& r, const T& sigma, const T& tau, int i, int j, double clip) {
+  const double beta = 1.0 / 1024.0;
+  const T log_rho = f_log2(f_clip_min(r, clip));
+  const bool live = val(log_rho) > log2(clip);
+  T expo = (4.0 / 3.0) * log_rho;
+  if (i > 0) {
+    const T log_g = f_log2(f_clip_min(sigma, clip)) / 2.0;
+    const T log_x = log_g - (4.0 / 3.0) * log_rho;
+    const T log_u = f_select(live, log_x - f_log2(1.0 + beta * f_exp2(log_x)) + log2(beta), cst<T>(0.0));
+    expo = expo + (double)i * log_u;
+  }
+  if (j > 0) {
+    const T log_tau = f_log2(f_clip_min(tau, clip));
+    const T log_1t = -((5.0 / 3.0) * log_rho - log_tau + (2.0 / 3.0) * log2(6.0 * PI * PI) + log2(3.0 / 5.0));
+    const T log_w = f_select(live, log_1t - f_log2(1.0 + beta * f_exp2(log_1t)) + log2(beta), cst<T>(0.0));
+    expo = expo + (double)j * log_w;
+  }
+  return f_exp2(expo);
+}
+
+}  // namespace pw
+}  // namespace gdft

@@ -1,0 +1,377 @@
+"""Differentiable ops over the C-ABI kernels (torch.autograd.Function bindings; no arithmetic of their own
+beyond bookkeeping).
+
+Every linear kernel is bound together with its transpose so that each is the other's VJP
+(`density_forward` <-> `density_transpose`, `coulomb_j` <-> its transpose, `hf_fock` <-> the HF
+energy-density contraction): autograd of any order closes over the same two kernels, which is what
+training through the SCF loop needs (grad_dft/evaluate.py:917-1038).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import GDFT_GRAD, GDFT_HF, GDFT_LAPL, GDFT_RHO, GDFT_TAU, check, lib, ptr, stream_ptr, workspace
+
+F64 = torch.float64
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != F64:
+        raise TypeError(f"graddft_b200 computes in float64, got {t.dtype}")
+    return t.contiguous()
+
+
+class PackedBasis:
+    """Planar, column-padded copy of the per-molecule constants ao / grad_ao / grad_n_ao[2] (/ chi).
+
+    Built once per molecule (they do not change across SCF iterations or training steps) by
+    gdft_pack_basis / gdft_pack_chi: planes[C, N, npad] with plane 0 = ao, 1..3 = d/dx,y,z ao,
+    4 = sum_i grad_n_ao[2][..., i]; chi_packed[W, 2, N, npad].
+    """
+
+    def __init__(self, ao: torch.Tensor, grad_ao: Optional[torch.Tensor] = None, grad2_ao: Optional[torch.Tensor] = None,
+                 chi: Optional[torch.Tensor] = None):
+        L = lib()
+        ao = _c(ao)
+        self.N, self.n = int(ao.shape[0]), int(ao.shape[1])
+        self.device = ao.device
+        self.npad = int(L.gdft_npad(self.n))
+        self.nplanes = 1 if grad_ao is None else (4 if grad2_ao is None else 5)
+        if grad2_ao is not None and grad_ao is None:
+            raise ValueError("grad2_ao needs grad_ao")
+        self.planes = torch.empty((self.nplanes, self.N, self.npad), dtype=F64, device=self.device)
+        grad_ao, grad2_ao = _c(grad_ao), _c(grad2_ao)
+        for t, shape in ((grad_ao, (self.N, self.n, 3)), (grad2_ao, (self.N, self.n, 3))):
+            if t is not None and tuple(t.shape) != shape:
+                raise TypeError(f"expected shape {shape}, got {tuple(t.shape)}")
+        check(L.gdft_pack_basis(stream_ptr(), self.N, self.n, ptr(ao), ptr(grad_ao), ptr(grad2_ao), ptr(self.planes), self.nplanes),
+              "gdft_pack_basis")
+        self.W = 0
+        self.chi_packed = None
+        if chi is not None:
+            self.set_chi(chi)
+
+    def set_chi(self, chi: torch.Tensor) -> None:
+        chi = _c(chi)
+        if chi.dim() != 4 or chi.shape[0] != self.N or chi.shape[2] != 2 or chi.shape[3] != self.n:
+            raise TypeError(f"chi must be [N, omega, 2, n], got {tuple(chi.shape)}")
+        self.W = int(chi.shape[1])
+        self.chi_packed = torch.empty((self.W, 2, self.N, self.npad), dtype=F64, device=self.device)
+        check(lib().gdft_pack_chi(stream_ptr(), self.N, self.n, self.W, ptr(chi), ptr(self.chi_packed)), "gdft_pack_chi")
+
+    def select_chi(self, indices) -> "PackedBasis":
+        """A view of this basis whose chi planes are the given omega indices (Molecule.select_HF_omegas)."""
+        other = object.__new__(PackedBasis)
+        other.__dict__.update(self.__dict__)
+        idx = list(indices)
+        if idx == list(range(self.W)):
+            return other
+        other.chi_packed = self.chi_packed[idx].contiguous()
+        other.W = len(idx)
+        return other
+
+
+# ---------------------------------------------------------------------------------------------------------
+# density family: L (rdm1 -> grid) and L^T (grid cotangents -> rdm1 cotangent)
+# ---------------------------------------------------------------------------------------------------------
+def _density_fwd_raw(basis: PackedBasis, rdm1: torch.Tensor, flags: int):
+    L = lib()
+    rdm1 = _c(rdm1)
+    if tuple(rdm1.shape) != (2, basis.n, basis.n):
+        raise TypeError(f"rdm1 must be [2, {basis.n}, {basis.n}], got {tuple(rdm1.shape)}")
+    N, dev = basis.N, basis.device
+    rho = torch.empty((N, 2), dtype=F64, device=dev) if flags & GDFT_RHO else None
+    grho = torch.empty((N, 2, 3), dtype=F64, device=dev) if flags & GDFT_GRAD else None
+    tau = torch.empty((N, 2), dtype=F64, device=dev) if flags & GDFT_TAU else None
+    lapl = torch.empty((N, 2), dtype=F64, device=dev) if flags & GDFT_LAPL else None
+    ehf = torch.empty((basis.W, 2, N), dtype=F64, device=dev) if flags & GDFT_HF else None
+    if (flags & GDFT_HF) and basis.chi_packed is None:
+        raise ValueError("Precomputed chi tensor has not been loaded.")
+    ws = workspace(L.gdft_workspace_bytes(_lib.OP_DENSITY_FWD, N, basis.n, flags, basis.W), dev)
+    check(L.gdft_density_fwd(stream_ptr(), N, basis.n, flags, basis.nplanes, ptr(basis.planes), ptr(rdm1),
+                             ptr(basis.chi_packed) if flags & GDFT_HF else None, basis.W,
+                             ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(ehf), ptr(ws), ws.numel()), "gdft_density_fwd")
+    return rho, grho, tau, lapl, ehf
+
+
+def _density_bwd_raw(basis: PackedBasis, flags: int, rho_bar, grho_bar, tau_bar, lapl_bar) -> torch.Tensor:
+    L = lib()
+    N, dev = basis.N, basis.device
+    out = torch.empty((2, basis.n, basis.n), dtype=F64, device=dev)
+    ws = workspace(L.gdft_workspace_bytes(_lib.OP_DENSITY_BWD, N, basis.n, flags, 0), dev)
+    check(L.gdft_density_bwd(stream_ptr(), N, basis.n, flags, basis.nplanes, ptr(basis.planes), ptr(_c(rho_bar)), ptr(_c(grho_bar)),
+                             ptr(_c(tau_bar)), ptr(_c(lapl_bar)), ptr(out), ptr(ws), ws.numel()), "gdft_density_bwd")
+    return out
+
+
+def _hf_fock_raw(basis: PackedBasis, g: torch.Tensor) -> torch.Tensor:
+    L = lib()
+    g = _c(g)
+    if tuple(g.shape) != (basis.W, 2, basis.N):
+        raise TypeError(f"g must be [{basis.W}, 2, {basis.N}], got {tuple(g.shape)}")
+    out = torch.empty((basis.W, 2, basis.n, basis.n), dtype=F64, device=basis.device)
+    ws = workspace(L.gdft_workspace_bytes(_lib.OP_HF_FOCK, basis.N, basis.n, 0, basis.W), basis.device)
+    check(L.gdft_hf_fock(stream_ptr(), basis.N, basis.n, basis.W, basis.nplanes, ptr(basis.planes), ptr(basis.chi_packed), ptr(g),
+                         ptr(out), ptr(ws), ws.numel()), "gdft_hf_fock")
+    return out
+
+
+class _DensityForward(Function):
+    @staticmethod
+    def forward(ctx, rdm1, basis, flags):
+        ctx.basis, ctx.flags = basis, flags
+        return _density_fwd_raw(basis, rdm1, flags)
+
+    @staticmethod
+    def backward(ctx, rho_bar, grho_bar, tau_bar, lapl_bar, ehf_bar):
+        basis = ctx.basis
+        flags = 0
+        if rho_bar is not None: flags |= GDFT_RHO
+        if grho_bar is not None: flags |= GDFT_GRAD
+        if tau_bar is not None: flags |= GDFT_TAU
+        if lapl_bar is not None: flags |= GDFT_LAPL
+        dbar = None
+        if flags:
+            dbar = density_transpose(basis, rho_bar, grho_bar, tau_bar, lapl_bar)
+        if ehf_bar is not None:
+            # e_HF[w,s,r] = -1/2 rowdot(chi_ws, ao D_s): its transpose is the HF Fock contraction summed over omega
+            v = hf_fock(basis, ehf_bar).sum(dim=0)
+            dbar = v if dbar is None else dbar + v
+        return dbar, None, None
+
+
+class _DensityTranspose(Function):
+    @staticmethod
+    def forward(ctx, basis, flags, rho_bar, grho_bar, tau_bar, lapl_bar):
+        ctx.basis, ctx.flags = basis, flags
+        return _density_bwd_raw(basis, flags, rho_bar, grho_bar, tau_bar, lapl_bar)
+
+    @staticmethod
+    def backward(ctx, dd):
+        rho, grho, tau, lapl, _ = _DensityForward.apply(dd, ctx.basis, ctx.flags)
+        return None, None, rho, grho, tau, lapl
+
+
+class _HFFock(Function):
+    @staticmethod
+    def forward(ctx, g, basis):
+        ctx.basis = basis
+        return _hf_fock_raw(basis, g)
+
+    @staticmethod
+    def backward(ctx, fbar):
+        basis = ctx.basis
+        rows = []
+        for w in range(basis.W):
+            ehf = _DensityForward.apply(fbar[w], basis, GDFT_HF)[4]
+            rows.append(ehf[w])
+        return torch.stack(rows, dim=0), None
+
+
+def density_forward(basis: PackedBasis, rdm1: torch.Tensor, flags: int):
+    """(rho, grad_rho, tau, lapl, ehf) for the quantities selected by `flags` (others None)."""
+    return _DensityForward.apply(rdm1, basis, flags)
+
+
+def density_transpose(basis: PackedBasis, rho_bar=None, grho_bar=None, tau_bar=None, lapl_bar=None) -> torch.Tensor:
+    flags = 0
+    if rho_bar is not None: flags |= GDFT_RHO
+    if grho_bar is not None: flags |= GDFT_GRAD
+    if tau_bar is not None: flags |= GDFT_TAU
+    if lapl_bar is not None: flags |= GDFT_LAPL
+    if not flags:
+        raise ValueError("density_transpose needs at least one cotangent")
+    return _DensityTranspose.apply(basis, flags, rho_bar, grho_bar, tau_bar, lapl_bar)
+
+
+def hf_fock(basis: PackedBasis, g: torch.Tensor) -> torch.Tensor:
+    """F[w,s,a,c] = -1/2 sum_r ao[r,a] g[w,s,r] chi[r,w,s,c]."""
+    if basis.chi_packed is None:
+        raise ValueError("Precomputed chi tensor has not been loaded.")
+    return _HFFock.apply(g, basis)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ERI sweep
+# ---------------------------------------------------------------------------------------------------------
+def _eri_j_raw(P, eri, want_energy=False):
+    L = lib()
+    P, eri = _c(P), _c(eri)
+    n = int(P.shape[0])
+    if tuple(eri.shape) != (n, n, n, n) or tuple(P.shape) != (n, n):
+        raise TypeError(f"rep_tensor must be [n,n,n,n] and rdm1 [n,n]; got {tuple(eri.shape)}, {tuple(P.shape)}")
+    J = torch.empty((n, n), dtype=F64, device=P.device)
+    EJ = torch.empty((1,), dtype=F64, device=P.device) if want_energy else None
+    check(L.gdft_eri_jk(stream_ptr(), n, ptr(eri), ptr(P), ptr(J), None, ptr(EJ), None, 0), "gdft_eri_jk")
+    return J, EJ
+
+
+def _eri_jt_raw(Jbar, eri):
+    L = lib()
+    Jbar, eri = _c(Jbar), _c(eri)
+    n = int(Jbar.shape[0])
+    out = torch.empty((n, n), dtype=F64, device=Jbar.device)
+    ws = workspace(L.gdft_workspace_bytes(_lib.OP_ERI_J, 0, n, 0, 0), Jbar.device)
+    check(L.gdft_eri_j_transpose(stream_ptr(), n, ptr(eri), ptr(Jbar), ptr(out), ptr(ws), ws.numel()), "gdft_eri_j_transpose")
+    return out
+
+
+class _CoulombJ(Function):
+    @staticmethod
+    def forward(ctx, P, eri):
+        ctx.save_for_backward(eri)
+        return _eri_j_raw(P, eri)[0]
+
+    @staticmethod
+    def backward(ctx, Jbar):
+        (eri,) = ctx.saved_tensors
+        return _CoulombJT.apply(Jbar, eri), None
+
+
+class _CoulombJT(Function):
+    @staticmethod
+    def forward(ctx, Jbar, eri):
+        ctx.save_for_backward(eri)
+        return _eri_jt_raw(Jbar, eri)
+
+    @staticmethod
+    def backward(ctx, g):
+        (eri,) = ctx.saved_tensors
+        return _CoulombJ.apply(g, eri), None
+
+
+def coulomb_j(P: torch.Tensor, eri: torch.Tensor) -> torch.Tensor:
+    return _CoulombJ.apply(P, eri)
+
+
+def coulomb_k(P: torch.Tensor, eri: torch.Tensor) -> torch.Tensor:
+    """K[p,r] = sum_qt (pq|rt) P[q,t]: same sweep, other index pairing (not in the reference; no VJP bound)."""
+    L = lib()
+    P, eri = _c(P.detach()), _c(eri.detach())
+    n = int(P.shape[0])
+    J = torch.empty((n, n), dtype=F64, device=P.device)
+    K = torch.empty((n, n), dtype=F64, device=P.device)
+    check(L.gdft_eri_jk(stream_ptr(), n, ptr(eri), ptr(P), ptr(J), ptr(K), None, None, 0), "gdft_eri_jk")
+    return K
+
+
+def coulomb_j_and_energy(P: torch.Tensor, eri: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """J and E_J = 1/2 <P,J> from one sweep (non-differentiable fast path used by the predictor)."""
+    J, EJ = _eri_j_raw(P.detach(), eri.detach(), want_energy=True)
+    return J, EJ[0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# XC quadrature
+# ---------------------------------------------------------------------------------------------------------
+class _XCIntegrate(Function):
+    @staticmethod
+    def forward(ctx, c, d, w, clip):
+        L = lib()
+        c, d, w = _c(c), _c(d), _c(w)
+        N, F = int(d.shape[0]), int(d.shape[1])
+        if c.dim() != 2 or c.shape[1] != F or c.shape[0] not in (1, N) or tuple(w.shape) != (N,):
+            raise TypeError(f"shapes: coefficients {tuple(c.shape)}, densities {tuple(d.shape)}, weights {tuple(w.shape)}")
+        E = torch.empty((1,), dtype=F64, device=d.device)
+        ws = workspace(L.gdft_workspace_bytes(_lib.OP_XC_INTEGRATE, N, 0, 0, 0), d.device)
+        check(L.gdft_xc_integrate_fwd(stream_ptr(), N, F, int(c.shape[0]), ptr(c), ptr(d), ptr(w), float(clip), ptr(E), ptr(ws), ws.numel()),
+              "gdft_xc_integrate_fwd")
+        ctx.save_for_backward(c, d, w)
+        ctx.clip = float(clip)
+        return E[0]
+
+    @staticmethod
+    def backward(ctx, Ebar):
+        c, d, w = ctx.saved_tensors
+        clip = ctx.clip
+        if torch.is_grad_enabled():
+            # higher-order request (create_graph=True): express the VJP with differentiable torch ops
+            e = (c * d).sum(dim=1)
+            wc = torch.where(w.abs() > clip, w, torch.zeros_like(w))
+            eb = torch.where(e.abs() > clip, Ebar * wc, torch.zeros_like(wc)).unsqueeze(1)
+            cbar = eb * d
+            if c.shape[0] == 1:
+                cbar = cbar.sum(dim=0, keepdim=True)
+            return (cbar if ctx.needs_input_grad[0] else None), (eb * c if ctx.needs_input_grad[1] else None), None, None
+        L = lib()
+        N, F = int(d.shape[0]), int(d.shape[1])
+        cbar = torch.empty_like(c) if ctx.needs_input_grad[0] else None
+        dbar = torch.empty_like(d) if ctx.needs_input_grad[1] else None
+        Eb = _c(Ebar.reshape(1))
+        ws = workspace(L.gdft_workspace_bytes(_lib.OP_XC_INTEGRATE, N, 0, 0, 0), d.device)
+        check(L.gdft_xc_integrate_bwd(stream_ptr(), N, F, int(c.shape[0]), ptr(c), ptr(d), ptr(w), clip, ptr(Eb), ptr(cbar), ptr(dbar),
+                                      ptr(ws), ws.numel()), "gdft_xc_integrate_bwd")
+        return cbar, dbar, None, None
+
+
+def xc_integrate(coefficients: torch.Tensor, densities: torch.Tensor, weights: torch.Tensor, clip: float = 1e-30) -> torch.Tensor:
+    """E = sum_r aclip(w_r) aclip(aclip(sum_f c[r,f] d[r,f]))."""
+    return _XCIntegrate.apply(coefficients, densities, weights, clip)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# closed-form per-point features
+# ---------------------------------------------------------------------------------------------------------
+class _Pointwise(Function):
+    @staticmethod
+    def forward(ctx, pw_id, clip, rho, grho, tau, lapl):
+        L = lib()
+        rho, grho, tau, lapl = _c(rho), _c(grho), _c(tau), _c(lapl)
+        N = int(rho.shape[0])
+        F = int(L.gdft_pointwise_ncols(pw_id))
+        out = torch.empty((N, F), dtype=F64, device=rho.device)
+        check(L.gdft_pointwise_fwd(stream_ptr(), N, pw_id, float(clip), ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(out)),
+              "gdft_pointwise_fwd")
+        ctx.pw_id, ctx.clip = pw_id, float(clip)
+        ctx.present = (grho is not None, tau is not None, lapl is not None)
+        ctx.save_for_backward(*[t for t in (rho, grho, tau, lapl) if t is not None])
+        return out
+
+    @staticmethod
+    def backward(ctx, out_bar):
+        L = lib()
+        saved = list(ctx.saved_tensors)
+        rho = saved.pop(0)
+        grho = saved.pop(0) if ctx.present[0] else None
+        tau = saved.pop(0) if ctx.present[1] else None
+        lapl = saved.pop(0) if ctx.present[2] else None
+        N = int(rho.shape[0])
+        need = ctx.needs_input_grad
+        rb = torch.empty_like(rho) if need[2] else None
+        gb = torch.empty_like(grho) if (grho is not None and need[3]) else None
+        tb = torch.empty_like(tau) if (tau is not None and need[4]) else None
+        lb = torch.empty_like(lapl) if (lapl is not None and need[5]) else None
+        check(L.gdft_pointwise_bwd(stream_ptr(), N, ctx.pw_id, ctx.clip, ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(_c(out_bar)),
+                                   ptr(rb), ptr(gb), ptr(tb), ptr(lb)), "gdft_pointwise_bwd")
+        return None, None, rb, gb, tb, lb
+
+
+def pointwise(name: str, rho, grad_rho=None, tau=None, lapl=None, clip: float = 1e-30) -> torch.Tensor:
+    """out[N,F] of one closed-form feature set (see _lib.PW_IDS); first-order differentiable."""
+    return _Pointwise.apply(_lib.PW_IDS[name], clip, rho, grad_rho, tau, lapl)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# predictor glue (no autograd: these sit after value_and_grad in grad_dft/train.py:148-215)
+# ---------------------------------------------------------------------------------------------------------
+def fock_assemble(h1e, J, rdm1_bar, clip: float = 1e-30) -> torch.Tensor:
+    L = lib()
+    h1e, J, rdm1_bar = _c(h1e), _c(J), _c(rdm1_bar)
+    n = int(h1e.shape[0])
+    fock = torch.empty((2, n, n), dtype=F64, device=h1e.device)
+    check(L.gdft_fock_assemble(stream_ptr(), n, ptr(h1e), ptr(J), ptr(rdm1_bar), float(clip), ptr(fock)), "gdft_fock_assemble")
+    return fock
+
+
+def fock_add_sym_(fock, V, clip: float = 1e-30) -> torch.Tensor:
+    L = lib()
+    V = _c(V)
+    n = int(fock.shape[1])
+    check(L.gdft_fock_add_sym(stream_ptr(), n, ptr(V), float(clip), ptr(fock)), "gdft_fock_add_sym")
+    return fock

@@ -1,0 +1,171 @@
+/*
+ * gdft_b200.h -- C-ABI of libgdft_b200.so: the B200 (sm_100a) kernels behind Grad DFT's
+ * per-SCF-iteration hot path.
+ *
+ * The reference (XanaduAI/GradDFT) has no plugin/FFI registry; its extension point is the set of
+ * jit-wrapped free functions in grad_dft/molecule.py that `Molecule` methods forward to, plus
+ * `Functional.xc_energy` (grad_dft/functional.py:219-253).  Each entry point below replaces the XLA
+ * lowering of one of those functions (cited per function).  Bindings (torch.autograd.Function via
+ * ctypes; jax.ffi + custom_vjp where JAX exists) live in graddft_b200/{ops,jax_ffi}.py and contain
+ * no arithmetic; INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; all arrays are IEEE float64,
+ *     row-major, last index fastest, in the reference's own layouts (grad_dft/molecule.py:76-102);
+ *   - every call is stream-ordered on `stream` (a cudaStream_t), never synchronises the device,
+ *     never allocates: scratch comes from the caller's `ws` (size from gdft_workspace_bytes);
+ *   - return value: 0 OK, 1 bad shape, 2 bad alignment, 3 workspace too small, 4 CUDA error
+ *     (code via gdft_last_cuda_error(), thread-local), 5 bad argument.  No exceptions, no global
+ *     mutable state: safe to call from any host thread on any stream/device;
+ *   - there is NO CPU implementation in this library.
+ */
+#ifndef GDFT_B200_H
+#define GDFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gdft_stream_t; /* cudaStream_t */
+
+enum gdft_status {
+  GDFT_OK = 0,
+  GDFT_BAD_SHAPE = 1,
+  GDFT_BAD_ALIGNMENT = 2,
+  GDFT_WORKSPACE_TOO_SMALL = 3,
+  GDFT_CUDA_ERROR = 4,
+  GDFT_BAD_ARGUMENT = 5
+};
+
+/* which grid quantities a density call produces / receives cotangents for */
+enum gdft_density_flags {
+  GDFT_RHO = 1,   /* rho[N,2]          grad_dft/molecule.py:388-409  */
+  GDFT_GRAD = 2,  /* grad_rho[N,2,3]   grad_dft/molecule.py:414-440  */
+  GDFT_TAU = 4,   /* tau[N,2]          grad_dft/molecule.py:479-502  */
+  GDFT_LAPL = 8,  /* lapl_rho[N,2]     grad_dft/molecule.py:445-474  */
+  GDFT_HF = 16    /* e_HF[W,2,N]       grad_dft/molecule.py:507-541  */
+};
+
+enum gdft_op {
+  GDFT_OP_DENSITY_FWD = 1,
+  GDFT_OP_DENSITY_BWD = 2,
+  GDFT_OP_HF_FOCK = 3,
+  GDFT_OP_ERI_J = 4,
+  GDFT_OP_XC_INTEGRATE = 5
+};
+
+/* closed-form per-point feature sets (grad_dft/popular_functionals.py, grad_dft/functional.py) */
+enum gdft_pointwise_id {
+  GDFT_PW_LSDA_X = 0,      /* 1 column   popular_functionals.py:29-50            */
+  GDFT_PW_B88_X = 1,       /* 1 column   popular_functionals.py:52-103           */
+  GDFT_PW_VWN_C = 2,       /* 1 column   popular_functionals.py:141-195          */
+  GDFT_PW_LYP_C = 3,       /* 1 column   popular_functionals.py:197-269          */
+  GDFT_PW_PW92_C = 4,      /* 1 column   popular_functionals.py:105-139          */
+  GDFT_PW_B3LYP_SET = 5,   /* 4 columns [lsda,b88,vwn,lyp]  popular_functionals.py:306-326 */
+  GDFT_PW_B88_SET = 6,     /* 2 columns [lsda,b88]          popular_functionals.py:277-284 */
+  GDFT_PW_DM21_INPUTS = 7, /* 7 columns  functional.py:504-531                   */
+  GDFT_PW_DM21_LDA = 8,    /* 1 column   functional.py:534-626 (functional_type="LDA") */
+  GDFT_PW_DM21_GGA = 9,    /* 2 columns  functional.py:534-626 ("GGA")           */
+  GDFT_PW_DM21_MGGA = 10,  /* 4 columns  functional.py:534-626 ("MGGA")          */
+  GDFT_PW_COUNT = 11
+};
+
+int gdft_version(void);
+int gdft_last_cuda_error(void);
+const char* gdft_status_string(int status);
+/* 1 if the current device is compute capability 10.x (the only supported target), else 0 */
+int gdft_device_supported(void);
+
+/* ---- packed basis -------------------------------------------------------------------------
+ * ao / grad_ao / grad_n_ao[2] are constant across SCF iterations and training steps, so they are
+ * re-laid-out ONCE into planar, column-padded planes packed[C][N][npad], npad = gdft_npad(n):
+ *   plane 0 = ao, 1..3 = d/dx,d/dy,d/dz ao (reference layout grad_ao[N,n,3] has xyz innermost,
+ *   grad_dft/interface/pyscf.py:826), plane 4 = sum_i grad_n_ao[2][:,:,i] (only that sum is ever
+ *   used: grad_dft/molecule.py:474).  C = 4, or 5 when grad2_ao != NULL.  Padding columns are zero. */
+int64_t gdft_npad(int64_t n);
+size_t gdft_packed_basis_bytes(int64_t N, int64_t n, int nplanes);
+int gdft_pack_basis(gdft_stream_t stream, int64_t N, int64_t n, const double* ao /*[N,n]*/,
+                    const double* grad_ao /*[N,n,3] or NULL*/, const double* grad2_ao /*[N,n,3] or NULL*/,
+                    double* packed /*[C,N,npad]*/, int nplanes);
+/* chi[N,W,2,n] (grad_dft/molecule.py:92) -> chi_packed[W,2,N,npad] */
+int gdft_pack_chi(gdft_stream_t stream, int64_t N, int64_t n, int W, const double* chi, double* chi_packed);
+
+size_t gdft_workspace_bytes(int op, int64_t N, int64_t n, int flags, int W);
+
+/* ---- K1: density family forward (linear map L: rdm1 -> grid quantities) --------------------
+ * replaces density / grad_density / kinetic_density / lapl_density / HF_energy_density
+ * (grad_dft/molecule.py:409,440,502,472-474,537-541).  T_s = ao D_s is formed tile-wise by FP64
+ * DMMA from TMA-staged tiles and contracted against the planes in the epilogue; T never reaches HBM.
+ * Outputs not selected by `flags` may be NULL. */
+int gdft_density_fwd(gdft_stream_t stream, int64_t N, int64_t n, int flags, int nplanes,
+                     const double* packed, const double* rdm1 /*[2,n,n]*/,
+                     const double* chi_packed /*[W,2,N,npad] or NULL*/, int W,
+                     double* rho /*[N,2]*/, double* grad_rho /*[N,2,3]*/, double* tau /*[N,2]*/,
+                     double* lapl /*[N,2]*/, double* ehf /*[W,2,N]*/, void* ws, size_t ws_bytes);
+
+/* ---- K2: density family transpose (L^T: grid cotangents -> rdm1 cotangent) ------------------
+ * the XLA transpose of the above inside value_and_grad (grad_dft/train.py:86,147):
+ *   Dbar_s = ao^T (rb_s*ao + 2 sum_j gb_sj*dj_ao + 2 lb_s*lap_ao) + sum_j dj_ao^T ((tb_s/2 + 2 lb_s)*dj_ao)
+ * un-symmetrised.  Cotangents not selected by `flags` may be NULL.  Split-K over the grid with a
+ * deterministic two-stage reduction.  Its own VJP is gdft_density_fwd. */
+int gdft_density_bwd(gdft_stream_t stream, int64_t N, int64_t n, int flags, int nplanes,
+                     const double* packed, const double* rho_bar, const double* grad_rho_bar,
+                     const double* tau_bar, const double* lapl_bar, double* rdm1_bar /*[2,n,n]*/,
+                     void* ws, size_t ws_bytes);
+
+/* ---- K4: explicit exact-exchange Fock term ---------------------------------------------------
+ * F[w,s,a,c] = -1/2 sum_r ao[r,a] g[w,s,r] chi[r,w,s,c]   (grad_dft/molecule.py:606-613, 678-685) */
+int gdft_hf_fock(gdft_stream_t stream, int64_t N, int64_t n, int W, int nplanes, const double* packed,
+                 const double* chi_packed, const double* g /*[W,2,N]*/, double* fock /*[W,2,n,n]*/,
+                 void* ws, size_t ws_bytes);
+
+/* ---- K3: ERI sweep ---------------------------------------------------------------------------
+ * J[p,q] = sum_rt eri[p,q,r,t] P[r,t]  (coulomb_potential, grad_dft/molecule.py:811);
+ * optionally K[p,r] = sum_qt eri[p,q,r,t] P[q,t] from the same pass (not in the reference; see
+ * SURVEY.md section 0.3) and E_J = 1/2 <P,J> (grad_dft/molecule.py:781-783).  K and EJ may be NULL. */
+int gdft_eri_jk(gdft_stream_t stream, int64_t n, const double* eri /*[n,n,n,n]*/, const double* P /*[n,n]*/,
+                double* J /*[n,n]*/, double* K /*[n,n] or NULL*/, double* EJ /*[1] or NULL*/,
+                void* ws, size_t ws_bytes);
+/* cotangent of the sweep wrt P: Pbar[r,t] = sum_pq Jbar[p,q] eri[p,q,r,t] (exact for any eri) */
+int gdft_eri_j_transpose(gdft_stream_t stream, int64_t n, const double* eri, const double* Jbar,
+                         double* Pbar, void* ws, size_t ws_bytes);
+
+/* ---- K6: XC quadrature ------------------------------------------------------------------------
+ * E = sum_r aclip(w_r) aclip(aclip(sum_f c[r,f] d[r,f]))  (grad_dft/functional.py:251-253,342;
+ * aclip = abs_clip, grad_dft/molecule.py:687-689).  c_rows is 1 (constant functionals,
+ * grad_dft/popular_functionals.py:347) or N. */
+int gdft_xc_integrate_fwd(gdft_stream_t stream, int64_t N, int F, int64_t c_rows, const double* c,
+                          const double* d, const double* w, double clip, double* E /*[1]*/, void* ws,
+                          size_t ws_bytes);
+int gdft_xc_integrate_bwd(gdft_stream_t stream, int64_t N, int F, int64_t c_rows, const double* c,
+                          const double* d, const double* w, double clip, const double* E_bar /*[1]*/,
+                          double* c_bar /*[c_rows,F] or NULL*/, double* d_bar /*[N,F] or NULL*/,
+                          void* ws, size_t ws_bytes);
+
+/* ---- K5: closed-form per-point features --------------------------------------------------------
+ * out[N,F] for one of gdft_pointwise_id; inputs not used by the id may be NULL.  bwd returns the
+ * cotangents of the inputs for cotangent out_bar[N,F] (forward-mode dual numbers inside the kernel,
+ * with jnp.clip / jnp.where sub-gradient conventions). */
+int gdft_pointwise_ncols(int id);
+int gdft_pointwise_fwd(gdft_stream_t stream, int64_t N, int id, double clip, const double* rho,
+                       const double* grad_rho, const double* tau, const double* lapl, double* out);
+int gdft_pointwise_bwd(gdft_stream_t stream, int64_t N, int id, double clip, const double* rho,
+                       const double* grad_rho, const double* tau, const double* lapl,
+                       const double* out_bar, double* rho_bar, double* grad_rho_bar, double* tau_bar,
+                       double* lapl_bar);
+
+/* ---- predictor glue ----------------------------------------------------------------------------
+ * fock = aclip(1/2 (X + X^T)), X = aclip(h1e + J + Dbar)   (grad_dft/train.py:148-163) */
+int gdft_fock_assemble(gdft_stream_t stream, int64_t n, const double* h1e, const double* J,
+                       const double* rdm1_bar /*[2,n,n]*/, double clip, double* fock /*[2,n,n]*/);
+/* fock = aclip(fock + V + V^T)                              (grad_dft/train.py:205-206, 212-213) */
+int gdft_fock_add_sym(gdft_stream_t stream, int64_t n, const double* V /*[2,n,n]*/, double clip,
+                      double* fock /*[2,n,n]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDFT_B200_H */
