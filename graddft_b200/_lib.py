@@ -92,6 +92,15 @@ def ptr(t: torch.Tensor | None):
     return c_void_p(t.data_ptr())
 
 
+def wptr(t: torch.Tensor | None):
+    """Device pointer of a raw (uint8) workspace tensor (or NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise GdftError("graddft_b200 kernels need CUDA tensors (there is no CPU path)")
+    return c_void_p(t.data_ptr())
+
+
 def stream_ptr() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -134,12 +134,21 @@ template <int NV> GDFT_HD Dual<NV> f_pow(const Dual<NV>& x, double p) { return c
 template <int NV> GDFT_HD Dual<NV> f_clip_min(const Dual<NV>& x, double c) { return x.v >= c ? x : Make<Dual<NV>>::constant(c); }
 template <int NV> GDFT_HD Dual<NV> f_select(bool cond, const Dual<NV>& a, const Dual<NV>& b) { return cond ? a : b; }
 
+// 2^(4 log2(x) / 3), the reference's log-domain x^{4/3} (functional.py:1014-1016).  Value exactly as written
+// there; derivative (4/3) x^{1/3}, which stays finite (0) at x == 0 where differentiating through log2
+// would give 0 * inf (fully spin-polarised points).
+GDFT_HD double f_pow43_log2(double x) { return exp2(4.0 * log2(x) / 3.0); }
+template <int NV> GDFT_HD Dual<NV> f_pow43_log2(const Dual<NV>& x) {
+  const double l = log2(x.v);
+  return chain(x, exp2(4.0 * l / 3.0), (4.0 / 3.0) * exp2(l / 3.0));
+}
+
 template <typename T> GDFT_HD T cst(double c) { return Make<T>::constant(c); }
 
 // ---- spin interpolation -------------------------------------------------------------------------------
 constexpr double FZ_DEN = 0.51984209978974632953442121455650;  // 2 (2^{1/3} - 1)
 constexpr double FZ_PP0 = 1.70992093416136561756560043006;     // f''(0) = 8 / (9 * FZ_DEN)
-constexpr double LOG2_RS0 = -0.68904830706500979;              // log2((3/(4 pi))^{1/3})
+constexpr double LOG2_RS0 = -0.688844542917054;              // log2((3/(4 pi))^{1/3})
 
 // functional.py:973-979
 template <typename T> GDFT_HD T exchange_polarization(const T& eP, const T& eF, const T& ra, const T& rb) {
@@ -165,8 +174,8 @@ template <typename T> GDFT_HD T correlation_polarization(const T& eP, const T& e
   const T log_rs = LOG2_RS0 - log_rho / 3.0;
   const T zeta = f_select(val(rt) > clip, (ra - rb) / rt, cst<T>(0.0));
   const T alphac = pw_G(log_rs, 0.016887, 0.11125, 10.357, 3.6231, 0.88026, 0.49671);
-  const T zm = f_exp2(4.0 * f_log2(1.0 - zeta) / 3.0);
-  const T zp = f_exp2(4.0 * f_log2(1.0 + zeta) / 3.0);
+  const T zm = f_pow43_log2(1.0 - zeta);
+  const T zp = f_pow43_log2(1.0 + zeta);
   const T fz = (zm + zp - 2.0) / FZ_DEN;
   const T z2 = zeta * zeta;
   const T z4 = z2 * z2;

@@ -14,7 +14,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import GDFT_GRAD, GDFT_HF, GDFT_LAPL, GDFT_RHO, GDFT_TAU, check, lib, ptr, stream_ptr, workspace
+from ._lib import GDFT_GRAD, GDFT_HF, GDFT_LAPL, GDFT_RHO, GDFT_TAU, check, lib, ptr, stream_ptr, workspace, wptr
 
 F64 = torch.float64
 
@@ -96,7 +96,7 @@ def _density_fwd_raw(basis: PackedBasis, rdm1: torch.Tensor, flags: int):
     ws = workspace(L.gdft_workspace_bytes(_lib.OP_DENSITY_FWD, N, basis.n, flags, basis.W), dev)
     check(L.gdft_density_fwd(stream_ptr(), N, basis.n, flags, basis.nplanes, ptr(basis.planes), ptr(rdm1),
                              ptr(basis.chi_packed) if flags & GDFT_HF else None, basis.W,
-                             ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(ehf), ptr(ws), ws.numel()), "gdft_density_fwd")
+                             ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(ehf), wptr(ws), ws.numel()), "gdft_density_fwd")
     return rho, grho, tau, lapl, ehf
 
 
@@ -106,7 +106,7 @@ def _density_bwd_raw(basis: PackedBasis, flags: int, rho_bar, grho_bar, tau_bar,
     out = torch.empty((2, basis.n, basis.n), dtype=F64, device=dev)
     ws = workspace(L.gdft_workspace_bytes(_lib.OP_DENSITY_BWD, N, basis.n, flags, 0), dev)
     check(L.gdft_density_bwd(stream_ptr(), N, basis.n, flags, basis.nplanes, ptr(basis.planes), ptr(_c(rho_bar)), ptr(_c(grho_bar)),
-                             ptr(_c(tau_bar)), ptr(_c(lapl_bar)), ptr(out), ptr(ws), ws.numel()), "gdft_density_bwd")
+                             ptr(_c(tau_bar)), ptr(_c(lapl_bar)), ptr(out), wptr(ws), ws.numel()), "gdft_density_bwd")
     return out
 
 
@@ -118,7 +118,7 @@ def _hf_fock_raw(basis: PackedBasis, g: torch.Tensor) -> torch.Tensor:
     out = torch.empty((basis.W, 2, basis.n, basis.n), dtype=F64, device=basis.device)
     ws = workspace(L.gdft_workspace_bytes(_lib.OP_HF_FOCK, basis.N, basis.n, 0, basis.W), basis.device)
     check(L.gdft_hf_fock(stream_ptr(), basis.N, basis.n, basis.W, basis.nplanes, ptr(basis.planes), ptr(basis.chi_packed), ptr(g),
-                         ptr(out), ptr(ws), ws.numel()), "gdft_hf_fock")
+                         ptr(out), wptr(ws), ws.numel()), "gdft_hf_fock")
     return out
 
 
@@ -218,7 +218,7 @@ def _eri_jt_raw(Jbar, eri):
     n = int(Jbar.shape[0])
     out = torch.empty((n, n), dtype=F64, device=Jbar.device)
     ws = workspace(L.gdft_workspace_bytes(_lib.OP_ERI_J, 0, n, 0, 0), Jbar.device)
-    check(L.gdft_eri_j_transpose(stream_ptr(), n, ptr(eri), ptr(Jbar), ptr(out), ptr(ws), ws.numel()), "gdft_eri_j_transpose")
+    check(L.gdft_eri_j_transpose(stream_ptr(), n, ptr(eri), ptr(Jbar), ptr(out), wptr(ws), ws.numel()), "gdft_eri_j_transpose")
     return out
 
 
@@ -280,7 +280,7 @@ class _XCIntegrate(Function):
             raise TypeError(f"shapes: coefficients {tuple(c.shape)}, densities {tuple(d.shape)}, weights {tuple(w.shape)}")
         E = torch.empty((1,), dtype=F64, device=d.device)
         ws = workspace(L.gdft_workspace_bytes(_lib.OP_XC_INTEGRATE, N, 0, 0, 0), d.device)
-        check(L.gdft_xc_integrate_fwd(stream_ptr(), N, F, int(c.shape[0]), ptr(c), ptr(d), ptr(w), float(clip), ptr(E), ptr(ws), ws.numel()),
+        check(L.gdft_xc_integrate_fwd(stream_ptr(), N, F, int(c.shape[0]), ptr(c), ptr(d), ptr(w), float(clip), ptr(E), wptr(ws), ws.numel()),
               "gdft_xc_integrate_fwd")
         ctx.save_for_backward(c, d, w)
         ctx.clip = float(clip)
@@ -306,7 +306,7 @@ class _XCIntegrate(Function):
         Eb = _c(Ebar.reshape(1))
         ws = workspace(L.gdft_workspace_bytes(_lib.OP_XC_INTEGRATE, N, 0, 0, 0), d.device)
         check(L.gdft_xc_integrate_bwd(stream_ptr(), N, F, int(c.shape[0]), ptr(c), ptr(d), ptr(w), clip, ptr(Eb), ptr(cbar), ptr(dbar),
-                                      ptr(ws), ws.numel()), "gdft_xc_integrate_bwd")
+                                      wptr(ws), ws.numel()), "gdft_xc_integrate_bwd")
         return cbar, dbar, None, None
 
 

@@ -505,7 +505,7 @@ def predict_b3lyp(mol: dict, clip: float = CLIP):
     E = xc_energy(c, b3lyp_combine(feats, ehf), mol["weights"], clip)  # molecule.py:600-604 (no aclip on densities here)
     (g,) = torch.autograd.grad(E, ehf)
     v = HF_fock(chi, g, ao).sum(dim=0)
-    fock = abs_clip(fock + v + v.transpose(1, 2), clip)
+    fock = abs_clip(fock + (v + v.transpose(1, 2)), clip)  # train.py:205,212: fock += V + V^T
     return energy, abs_clip(fock, clip)
 
 
@@ -531,13 +531,13 @@ def predict_dm21(mol: dict, params, clip: float = CLIP):
     E = xc_energy(dm21_mlp(params, cinputs), dm21_combine_densities(grad_densities, ehf), w, clip)
     (g,) = torch.autograd.grad(E, ehf)
     v = HF_fock(chi, g, ao).sum(dim=0)
-    fock = abs_clip(fock + v + v.transpose(1, 2), clip)
+    fock = abs_clip(fock + (v + v.transpose(1, 2)), clip)  # train.py:205,212: fock += V + V^T
     # coefficient_input_grads: d E / d ehf through the network inputs only (molecule.py:672-676)
     ehf = ehf0.clone().requires_grad_(True)
     E = xc_energy(dm21_mlp(params, dm21_combine_cinputs(grad_cinputs, ehf)), densities, w, clip)
     (g,) = torch.autograd.grad(E, ehf)
     v = HF_fock(chi, g, ao).sum(dim=0)
-    fock = abs_clip(fock + v + v.transpose(1, 2), clip)
+    fock = abs_clip(fock + (v + v.transpose(1, 2)), clip)  # train.py:205,212: fock += V + V^T
     return energy, abs_clip(fock, clip)
 
 
