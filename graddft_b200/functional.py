@@ -1,0 +1,283 @@
+"""`Functional`, `NeuralFunctional`, `DM21` and the DM21 feature functions of grad_dft/functional.py.
+
+Same names and argument meaning as the reference (grad_dft/functional.py:48-342 for `Functional`,
+:345-498 `NeuralFunctional`, :504-758 the DM21 feature/combination functions, :761-822 `DM21`), with
+torch tensors and `params` as a plain dict pytree of tensors (``{"params": {...}}`` accepted too).  The
+grid-sized arithmetic (quadrature, closed-form features) is C-ABI kernel calls through `ops`; the
+coefficient network is user-level host-framework code (float64 torch matmuls -> cuBLAS), as upstream where
+it is flax code.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .molecule import Grid, Molecule, abs_clip
+
+Array = torch.Tensor
+F64 = torch.float64
+
+
+def stop_gradient(x: Array) -> Array:
+    return x.detach()
+
+
+def _is_closed_form_row(c: Array) -> bool:
+    return c.dim() == 2 and c.shape[0] == 1
+
+
+@dataclass
+class Functional:
+    """grad_dft/functional.py:48-342.  `coefficients(self, cinputs)` and the feature callables keep the
+    reference's calling conventions; `needs` is an optional hint (not upstream) naming the grid
+    quantities the feature functions will ask the molecule for, so that they are produced by one fused
+    kernel launch instead of one launch each."""
+
+    coefficients: Callable
+    energy_densities: Optional[Callable]
+    coefficient_inputs: Optional[Callable] = None
+    nograd_densities: Optional[Callable] = None
+    densitygrads: Optional[Callable] = None
+    combine_densities: Optional[Callable] = None
+    nograd_coefficient_inputs: Optional[Callable] = None
+    coefficient_input_grads: Optional[Callable] = None
+    combine_inputs: Optional[Callable] = None
+    is_xc: bool = True
+    exchange_mask: Any = None
+    needs: Sequence[str] = ()
+    needs_omegas: Optional[Sequence[float]] = None
+
+    # flax's Module.apply(params, *inputs): bind params, then __call__
+    def apply(self, params, coefficient_inputs, **kwargs) -> Array:
+        return self.coefficients(self, coefficient_inputs)
+
+    def __call__(self, coefficient_inputs) -> Array:
+        return self.coefficients(self, coefficient_inputs)
+
+    def _prefetch(self, atoms) -> None:
+        if self.needs and hasattr(atoms, "prefetch"):
+            m = atoms._memo()
+            from ._lib import GDFT_GRAD, GDFT_LAPL, GDFT_RHO, GDFT_TAU
+            flag_of = {"rho": GDFT_RHO, "grad": GDFT_GRAD, "tau": GDFT_TAU, "lapl": GDFT_LAPL}
+            if any(flag_of[nm] not in m for nm in self.needs):
+                atoms.prefetch(*self.needs, omegas=self.needs_omegas)
+
+    def compute_densities(self, atoms, clip_cte: float = 1e-30, *args, **kwargs) -> Array:
+        """grad_dft/functional.py:160-185."""
+        self._prefetch(atoms)
+        if self.nograd_densities and self.energy_densities:
+            densities = self.energy_densities(atoms, *args, **kwargs)
+            nograd_densities = stop_gradient(self.nograd_densities(atoms, *args, **kwargs))
+            densities = self.combine_densities(densities, nograd_densities)
+        elif self.energy_densities:
+            densities = self.energy_densities(atoms, *args, **kwargs)
+        elif self.nograd_densities:
+            densities = stop_gradient(self.nograd_densities(atoms, *args, **kwargs))
+        return abs_clip(densities, clip_cte)
+
+    def compute_coefficient_inputs(self, atoms, *args, **kwargs) -> Optional[Array]:
+        """grad_dft/functional.py:187-217."""
+        self._prefetch(atoms)
+        if self.nograd_coefficient_inputs and self.coefficient_inputs:
+            cinputs = self.coefficient_inputs(atoms, *args, **kwargs)
+            nograd_cinputs = stop_gradient(self.nograd_coefficient_inputs(atoms, *args, **kwargs))
+            cinputs = self.combine_inputs(cinputs, nograd_cinputs)
+        elif self.coefficient_inputs:
+            cinputs = self.coefficient_inputs(atoms, *args, **kwargs)
+        elif self.nograd_coefficient_inputs:
+            cinputs = stop_gradient(self.nograd_coefficient_inputs(atoms, *args, **kwargs))
+        else:
+            cinputs = None
+        return cinputs
+
+    def xc_energy(self, params, grid: Grid, coefficient_inputs, densities: Array, clip_cte: float = 1e-30, **kwargs) -> Array:
+        """grad_dft/functional.py:219-253: e_r = sum_f c[r,f] d[r,f]; abs_clip; quadrature with clipped weights.
+        One fused kernel (gdft_xc_integrate_fwd); its VJP is gdft_xc_integrate_bwd."""
+        coefficients = self.apply(params, coefficient_inputs, **kwargs)
+        if coefficients.dim() == 1:
+            coefficients = coefficients.unsqueeze(-1) if coefficients.shape[0] == densities.shape[0] else coefficients.unsqueeze(0)
+        if coefficients.shape[-1] == 1 and densities.shape[1] != 1:
+            coefficients = coefficients.expand(coefficients.shape[0], densities.shape[1])  # einsum "rf,rf->r" broadcast
+        return ops.xc_integrate(coefficients.to(densities.dtype), densities, grid.weights, clip_cte)
+
+    def energy(self, params, atoms, *args, **kwargs) -> Array:
+        """grad_dft/functional.py:255-288."""
+        densities = self.compute_densities(atoms, *args, **kwargs)
+        cinputs = self.compute_coefficient_inputs(atoms, *args)
+        energy = self.xc_energy(params, atoms.grid, cinputs, densities, **kwargs)
+        if self.is_xc:
+            energy = energy + atoms.nonXC()
+        return energy
+
+    def energy_xc_only(self, params, atoms, *args, **kwargs) -> Array:
+        """grad_dft/functional.py:290-314."""
+        densities = self.compute_densities(atoms, *args, **kwargs)
+        cinputs = self.compute_coefficient_inputs(atoms, *args)
+        return self.xc_energy(params, atoms.grid, cinputs, densities, **kwargs)
+
+    def _integrate(self, energy_density: Array, gridweights: Array, precision=None, clip_cte: float = 1e-30) -> Array:
+        """grad_dft/functional.py:316-342 (kept for constraint-style callers that integrate their own density)."""
+        ones = torch.ones((1, 1), dtype=energy_density.dtype, device=energy_density.device)
+        return ops.xc_integrate(ones, energy_density.reshape(-1, 1), gridweights, clip_cte)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# neural functionals
+# ---------------------------------------------------------------------------------------------------------
+def _unwrap(params):
+    return params["params"] if isinstance(params, dict) and "params" in params and isinstance(params["params"], dict) else params
+
+
+@dataclass
+class NeuralFunctional(Functional):
+    """grad_dft/functional.py:345-498.  `coefficients(self, cinputs)` may call `self.dense(i, x)`,
+    `self.layer_norm(i, x)` and `self.head(x, ...)`, which read the bound parameter dict."""
+
+    activation: Callable = torch.nn.functional.gelu
+    param_dtype: torch.dtype = F64
+
+    def apply(self, params, coefficient_inputs, **kwargs) -> Array:
+        object.__setattr__(self, "_bound", _unwrap(params))
+        object.__setattr__(self, "_dense_i", 0)
+        object.__setattr__(self, "_ln_i", 0)
+        try:
+            return self.coefficients(self, coefficient_inputs)
+        finally:
+            object.__setattr__(self, "_bound", None)
+
+    # flax names submodules Dense_0, Dense_1, ... / LayerNorm_0, ... in call order
+    def dense(self, x: Array) -> Array:
+        i = self._dense_i
+        object.__setattr__(self, "_dense_i", i + 1)
+        p = self._bound
+        return x @ p[f"Dense_{i}.kernel"] + p[f"Dense_{i}.bias"]
+
+    def layer_norm(self, x: Array, eps: float = 1e-6) -> Array:
+        i = self._ln_i
+        object.__setattr__(self, "_ln_i", i + 1)
+        p = self._bound
+        mu = x.mean(dim=-1, keepdim=True)
+        var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+        return (x - mu) * torch.rsqrt(var + eps) * p[f"LayerNorm_{i}.scale"] + p[f"LayerNorm_{i}.bias"]
+
+    def head(self, x: Array, local_features: int, sigmoid_scale_factor: float) -> Array:
+        """grad_dft/functional.py:407-419: dense -> sigmoid(x/s) * s."""
+        x = self.dense(x)
+        return sigmoid_scale_factor * torch.sigmoid(x / sigmoid_scale_factor)
+
+
+def canonicalize_inputs(x):
+    """grad_dft/functional.py:931-947."""
+    if isinstance(x, (tuple, list)):
+        x = torch.cat(list(x), dim=1)
+    if x.dim() == 1:
+        x = x.unsqueeze(1)
+    return x
+
+
+# ---- DM21 features (grad_dft/functional.py:504-758) -------------------------------------------------
+def dm21_coefficient_inputs(molecule: Molecule, clip_cte: float = 1e-30, *_, **__) -> Array:
+    """grad_dft/functional.py:504-531: [rho_a, rho_b, |g_a+g_b|^2, |g_a|^2, |g_b|^2, tau_a, tau_b]."""
+    return ops.pointwise("DM21_INPUTS", molecule.density(), molecule.grad_density(), molecule.kinetic_density(), None, clip_cte)
+
+
+def dm21_densities(molecule: Molecule, functional_type: Optional[str] = "LDA", clip_cte: float = 1e-30, *_, **__) -> Array:
+    """grad_dft/functional.py:534-626."""
+    kind = {"LDA": "DM21_LDA", "DM21": "DM21_LDA", "GGA": "DM21_GGA", "MGGA": "DM21_MGGA"}[functional_type]
+    rho = molecule.density()
+    grho = molecule.grad_density() if kind != "DM21_LDA" else None
+    tau = molecule.kinetic_density() if kind == "DM21_MGGA" else None
+    return ops.pointwise(kind, rho, grho, tau, None, clip_cte)
+
+
+def dm21_combine_cinputs(cinputs: Array, ehf: Array) -> Array:
+    """grad_dft/functional.py:628-649: HF features appended by spin, [w0 a, w1 a, w0 b, w1 b]."""
+    return torch.cat([cinputs, ehf[:, 0].T, ehf[:, 1].T], dim=1)
+
+
+def dm21_combine_densities(densities: Array, ehf: Array) -> Array:
+    """grad_dft/functional.py:651-675: one spin-summed HF column per omega."""
+    return torch.cat([densities] + [ehf[i].sum(dim=0, keepdim=True).T for i in range(ehf.shape[0])], dim=1)
+
+
+def dm21_hfgrads_densities(functional, params, atoms, ehf, coefficient_inputs, densities_wout_hf, omegas=(0.0, 0.4)) -> Array:
+    """grad_dft/functional.py:677-717."""
+    vxc_hf = atoms.HF_density_grad_2_Fock(functional, params, omegas, ehf, coefficient_inputs, densities_wout_hf)
+    return vxc_hf.sum(dim=0)
+
+
+def dm21_hfgrads_cinputs(functional, params, atoms, ehf, cinputs_wout_hf, densities, omegas=(0.0, 0.4)) -> Array:
+    """grad_dft/functional.py:719-758."""
+    vxc_hf = atoms.HF_coefficient_input_grad_2_Fock(functional, params, omegas, ehf, cinputs_wout_hf, densities)
+    return vxc_hf.sum(dim=0)
+
+
+_DM21_OMEGAS = (0.0, 0.4)
+
+
+def _dm21_default_nn(instance, rhoinputs, *_, **__):
+    """grad_dft/functional.py:793-822: log|x|+eps -> dense -> tanh -> 6 x (dense + res -> LayerNorm -> act) -> head."""
+    x = canonicalize_inputs(rhoinputs)
+    x = torch.log(torch.abs(x) + instance.squash_offset)
+    x = torch.tanh(instance.dense(x))
+    for _ in instance.layer_widths:
+        res = x
+        x = instance.dense(x) + res
+        x = instance.layer_norm(x)
+        x = instance.activation(x)
+    return instance.head(x, instance.local_features, instance.sigmoid_scale_factor)
+
+
+@dataclass
+class DM21(NeuralFunctional):
+    """grad_dft/functional.py:761-928 (architecture and feature wiring; the TF-checkpoint importer is out of
+    scope -- TensorFlow is absent -- so weights come from `generate_DM21_weights`' seeded stand-in)."""
+
+    coefficients: Callable = _dm21_default_nn
+    energy_densities: Callable = dm21_densities
+    nograd_densities: Callable = lambda atoms, *_, **__: atoms.HF_energy_density(_DM21_OMEGAS)
+    densitygrads: Callable = lambda self, params, atoms, nograd_densities, cinputs, grad_densities, *_, **__: dm21_hfgrads_densities(
+        self, params, atoms, nograd_densities, cinputs, grad_densities, _DM21_OMEGAS)
+    combine_densities: Callable = dm21_combine_densities
+    coefficient_inputs: Callable = dm21_coefficient_inputs
+    nograd_coefficient_inputs: Callable = lambda atoms, *_, **__: atoms.HF_energy_density(_DM21_OMEGAS)
+    coefficient_input_grads: Callable = lambda self, params, atoms, nograd_cinputs, grad_cinputs, densities, *_, **__: dm21_hfgrads_cinputs(
+        self, params, atoms, nograd_cinputs, grad_cinputs, densities, _DM21_OMEGAS)
+    combine_inputs: Callable = dm21_combine_cinputs
+    activation: Callable = torch.nn.functional.elu
+    squash_offset: float = 1e-4
+    layer_widths: Sequence[int] = (256, 256, 256, 256, 256, 256)
+    local_features: int = 3
+    sigmoid_scale_factor: float = 2.0
+    needs: Sequence[str] = ("rho", "grad", "tau")
+    needs_omegas: Optional[Sequence[float]] = _DM21_OMEGAS
+
+    def default_nn(self, rhoinputs, *a, **k):
+        return _dm21_default_nn(self, rhoinputs)
+
+    def generate_DM21_weights(self, n_input_features: int = 11, seed: int = 1984, device=None) -> Dict[str, Array]:
+        """Seeded stand-in for the DeepMind checkpoint (grad_dft/functional.py:824-928 reads a TF SavedModel,
+        which needs TensorFlow): He-normal kernels, zero biases, identity added to the square residual kernels
+        (functional.py:913-921), LayerNorm scale 1 / bias 0."""
+        g = torch.Generator().manual_seed(seed)
+        widths = list(self.layer_widths)
+        p: Dict[str, Array] = {}
+
+        def he(i, o):
+            return torch.randn(i, o, generator=g, dtype=F64) * math.sqrt(2.0 / i)
+
+        p["Dense_0.kernel"], p["Dense_0.bias"] = he(n_input_features, widths[0]), torch.zeros(widths[0], dtype=F64)
+        for k, wdt in enumerate(widths):
+            p[f"Dense_{k + 1}.kernel"] = he(wdt, wdt) + torch.eye(wdt, dtype=F64)
+            p[f"Dense_{k + 1}.bias"] = torch.zeros(wdt, dtype=F64)
+            p[f"LayerNorm_{k}.scale"] = torch.ones(wdt, dtype=F64)
+            p[f"LayerNorm_{k}.bias"] = torch.zeros(wdt, dtype=F64)
+        p[f"Dense_{len(widths) + 1}.kernel"] = he(widths[-1], self.local_features)
+        p[f"Dense_{len(widths) + 1}.bias"] = torch.zeros(self.local_features, dtype=F64)
+        if device is not None:
+            p = {k: v.to(device) for k, v in p.items()}
+        return p

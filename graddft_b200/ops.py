@@ -66,15 +66,22 @@ class PackedBasis:
         check(lib().gdft_pack_chi(stream_ptr(), self.N, self.n, self.W, ptr(chi), ptr(self.chi_packed)), "gdft_pack_chi")
 
     def select_chi(self, indices) -> "PackedBasis":
-        """A view of this basis whose chi planes are the given omega indices (Molecule.select_HF_omegas)."""
-        other = object.__new__(PackedBasis)
-        other.__dict__.update(self.__dict__)
-        idx = list(indices)
-        if idx == list(range(self.W)):
-            return other
-        other.chi_packed = self.chi_packed[idx].contiguous()
-        other.W = len(idx)
-        return other
+        """A view of this basis whose chi planes are the given omega indices (Molecule.select_HF_omegas).
+        Contiguous ascending index ranges are zero-copy slices; other selections are gathered once and kept."""
+        idx = tuple(int(i) for i in indices)
+        if idx == tuple(range(self.W)):
+            return self
+        cache = self.__dict__.setdefault("_selected", {})
+        if idx not in cache:
+            other = object.__new__(PackedBasis)
+            other.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_selected"})
+            if idx == tuple(range(idx[0], idx[0] + len(idx))):
+                other.chi_packed = self.chi_packed[idx[0]:idx[0] + len(idx)]
+            else:
+                other.chi_packed = self.chi_packed[list(idx)].contiguous()
+            other.W = len(idx)
+            cache[idx] = other
+        return cache[idx]
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -1,0 +1,125 @@
+"""`energy_predictor` -- grad_dft/train.py:34-218, re-stated over the kernel-backed ops.
+
+`predict(params, molecule) -> (energy, fock)` follows the reference step by step: value-and-grad of the XC
+energy with respect to rdm1 (train.py:86-121,147), h1e + J (148), E = Exc + nonXC (150), clip / symmetrise /
+clip (161-163), the explicit exact-exchange Fock terms of hybrids with `fock += V + V^T` and a clip after each
+(200-213), final clip (215).  J and E_J come from one ERI sweep (the reference sweeps twice; under jit XLA
+merges them -- SURVEY.md Appendix B).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from . import ops
+from .functional import Functional, stop_gradient
+from .molecule import Molecule, abs_clip
+
+Array = torch.Tensor
+
+
+def _requires_grad(params) -> bool:
+    if isinstance(params, torch.Tensor):
+        return params.requires_grad
+    if isinstance(params, dict):
+        return any(_requires_grad(v) for v in params.values())
+    if isinstance(params, (list, tuple)):
+        return any(_requires_grad(v) for v in params)
+    return False
+
+
+def xc_energy_and_grads(functional: Functional, params, rdm1: Array, atoms: Molecule, *args, create_graph: Optional[bool] = None,
+                        **functional_kwargs) -> Tuple[Array, Array, Molecule]:
+    """value_and_grad(argnums=1) of the XC energy (grad_dft/train.py:86-121): one "XC build" = forward
+    (densities -> features -> E_xc) + VJP (-> V_xc [2,n,n], un-symmetrised).  Also returns the molecule
+    carrying the differentiated rdm1 (its cached grid quantities are reused by the hybrid terms)."""
+    if create_graph is None:
+        create_graph = torch.is_grad_enabled() and (_requires_grad(params) or rdm1.requires_grad)
+    leaf = rdm1 if (create_graph and rdm1.requires_grad) else rdm1.detach().requires_grad_(True)
+    with torch.enable_grad():
+        at = atoms.replace(rdm1=leaf)
+        densities = functional.compute_densities(at, *args, **functional_kwargs)
+        cinputs = functional.compute_coefficient_inputs(at, *args)
+        exc = functional.xc_energy(params, at.grid, cinputs, densities, **functional_kwargs)
+        (fock_xc,) = torch.autograd.grad(exc, leaf, create_graph=create_graph)
+    if not create_graph:
+        exc = exc.detach()
+    return exc, fock_xc, at
+
+
+def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: float = 1e-30, **kwargs) -> Callable:
+    """grad_dft/train.py:34-218."""
+    if nlc_functional is not None:
+        raise NotImplementedError("nlc_functional: the reference path raises NameError here (train.py:117-120)")
+
+    def predict(params, atoms: Molecule, *args) -> Tuple[Array, Array]:
+        exc, fock_xc, at = xc_energy_and_grads(functional, params, atoms.rdm1, atoms, *args)
+        differentiable = exc.requires_grad
+        P = atoms.rdm1.sum(dim=0)
+        if differentiable or atoms.rdm1.requires_grad:
+            J = ops.coulomb_j(P, atoms.rep_tensor)
+            EJ = (P * J).sum() / 2.0
+        else:
+            J, EJ = ops.coulomb_j_and_energy(P, atoms.rep_tensor)
+        energy = exc + (atoms.nuclear_repulsion + (P * atoms.h1e).sum() + EJ)  # train.py:150, molecule.py:727-733
+
+        if fock_xc.requires_grad or J.requires_grad:
+            fock = atoms.h1e + J + fock_xc
+            fock = abs_clip(fock, clip_cte)
+            fock = 0.5 * (fock + fock.transpose(1, 2))
+            fock = abs_clip(fock, clip_cte)
+        else:
+            fock = ops.fock_assemble(atoms.h1e, J, fock_xc, clip_cte)  # train.py:148-163 in one kernel
+
+        # train.py:165-198: features for the explicit terms (cached on `at`, so nothing is recomputed)
+        with torch.set_grad_enabled(differentiable):
+            if functional.energy_densities and functional.densitygrads:
+                grad_densities = functional.energy_densities(at, *args, **kwargs)
+                nograd_densities = stop_gradient(functional.nograd_densities(at, *args, **kwargs))
+                densities = functional.combine_densities(grad_densities, nograd_densities)
+            elif functional.energy_densities:
+                grad_densities, nograd_densities = functional.energy_densities(at, *args, **kwargs), None
+                densities = grad_densities
+            elif functional.densitygrads:
+                grad_densities, nograd_densities = None, stop_gradient(functional.nograd_densities(at, *args, **kwargs))
+                densities = nograd_densities
+            else:
+                densities, grad_densities, nograd_densities = None, None, None
+
+            if functional.coefficient_input_grads and functional.coefficient_inputs:
+                grad_cinputs = functional.coefficient_inputs(at, *args, **kwargs)
+                nograd_cinputs = stop_gradient(functional.nograd_coefficient_inputs(at, *args, **kwargs))
+                cinputs = functional.combine_inputs(grad_cinputs, nograd_cinputs)
+            elif functional.coefficient_inputs:
+                grad_cinputs, nograd_cinputs = functional.coefficient_inputs(at, *args, **kwargs), None
+                cinputs = grad_cinputs
+            elif functional.coefficient_input_grads:
+                grad_cinputs, nograd_cinputs = None, stop_gradient(functional.nograd_coefficient_inputs(at, *args, **kwargs))
+                cinputs = nograd_cinputs
+            else:
+                cinputs, grad_cinputs, nograd_cinputs = None, None, None
+
+        def detached(t):
+            return t.detach() if isinstance(t, torch.Tensor) else t
+
+        if functional.densitygrads:
+            vxc_expl = functional.densitygrads(functional, params, at, nograd_densities, detached(cinputs), detached(grad_densities))
+            fock = _add_sym(fock, vxc_expl, clip_cte)
+        if functional.coefficient_input_grads:
+            vxc_expl = functional.coefficient_input_grads(functional, params, at, nograd_cinputs, detached(grad_cinputs), detached(densities))
+            fock = _add_sym(fock, vxc_expl, clip_cte)
+        fock = abs_clip(fock, clip_cte)
+        return energy, fock
+
+    return predict
+
+
+def _add_sym(fock: Array, v: Array, clip_cte: float) -> Array:
+    """fock += V + V^T; abs_clip   (train.py:205-206, 212-213)."""
+    if fock.requires_grad or v.requires_grad:
+        return abs_clip(fock + (v + v.transpose(1, 2)), clip_cte)
+    return ops.fock_add_sym_(fock, v, clip_cte)
+
+
+molecule_predictor = energy_predictor  # name used in the notebooks' prose

@@ -1,0 +1,119 @@
+"""energy_predictor / Functional.energy through the public API vs the CPU oracle (train.py:124-216 restated)."""
+import pytest
+import torch
+
+import oracle
+import graddft_b200 as gd
+from graddft_b200.synthetic import synthetic_molecule
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+E_TOL = 1e-8      # Ha, BASELINE.json / tests/integration/molecules/test_non_xc_energy.py:42
+F_RTOL = 1e-7     # relative, BASELINE.json
+
+
+def relerr(a, b):
+    return float((a.cpu() - b).abs().max() / (b.abs().max() + 1e-300))
+
+
+FUNCS = {"LSDA": gd.LSDA, "B88": gd.B88, "VWN": gd.VWN, "LYP": gd.LYP, "PW92": gd.PW92}
+
+
+@pytest.mark.parametrize("name", list(FUNCS))
+@pytest.mark.parametrize("N,n,seed", [(3000, 12, 1984), (2500, 43, 1993)])
+def test_semilocal_predictor(cuda_device, name, N, n, seed):
+    mol = synthetic_molecule(N, n, seed=seed, mask_frac=0.0)
+    e_ref, f_ref = oracle.predict_semilocal(mol, name)
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    e, f = gd.energy_predictor(FUNCS[name])(None, m)
+    assert abs(float(e) - float(e_ref)) < E_TOL
+    assert relerr(f, f_ref) < F_RTOL
+    # Functional.energy + autograd wrt rdm1 (grad_dft/functional.py:255-288; notebook 02 cells 30-35)
+    leaf = m.rdm1.clone().requires_grad_(True)
+    e2 = FUNCS[name].energy(None, m.replace(rdm1=leaf))
+    assert abs(float(e2) - float(e_ref)) < E_TOL
+    (g,) = torch.autograd.grad(e2, leaf)
+    D = mol["rdm1"].clone().requires_grad_(True)
+    e_o = oracle.xc_energy_of_rdm1(D, mol, name) + oracle.nonXC(D.sum(0), mol["h1e"], mol["rep_tensor"], mol["nuclear_repulsion"])
+    (g_ref,) = torch.autograd.grad(e_o, D)
+    assert relerr(g, g_ref) < F_RTOL
+
+
+@pytest.mark.parametrize("N,n,seed", [(3000, 12, 1984), (2500, 43, 1993)])
+def test_b3lyp_predictor(cuda_device, N, n, seed):
+    mol = synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0)
+    e_ref, f_ref = oracle.predict_b3lyp(mol)
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    e, f = gd.energy_predictor(gd.B3LYP)(None, m)
+    assert abs(float(e) - float(e_ref)) < E_TOL
+    assert relerr(f, f_ref) < F_RTOL
+    assert torch.equal(f, f.transpose(1, 2)) or relerr(f, f_ref.transpose(1, 2)) < F_RTOL
+
+
+@pytest.mark.parametrize("N,n,seed", [(2000, 12, 1984), (1500, 30, 1993)])
+def test_dm21_predictor(cuda_device, N, n, seed):
+    mol = synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0)
+    params = oracle.dm21_mlp_init(seed=seed)
+    e_ref, f_ref = oracle.predict_dm21(mol, params)
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    fun = gd.DM21()
+    p = {k: v.to(cuda_device) for k, v in params.items()}
+    e, f = gd.energy_predictor(fun)(p, m)
+    assert abs(float(e) - float(e_ref)) < E_TOL
+    assert relerr(f, f_ref) < F_RTOL
+    # gradient with respect to the network parameters (training step, train.py:312-359)
+    pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    D = mol["rdm1"]
+    e_o = oracle.xc_energy_of_rdm1(D, mol, "DM21", params=pl)
+    g_ref = torch.autograd.grad(e_o, list(pl.values()))
+    pd = {k: v.to(cuda_device).requires_grad_(True) for k, v in params.items()}
+    e_x = fun.energy_xc_only(pd, m)
+    g = torch.autograd.grad(e_x, list(pd.values()))
+    for a, b, k in zip(g, g_ref, pd):
+        assert relerr(a, b) < 1e-6 or float(b.abs().max()) < 1e-14, k
+
+
+def test_masked_rows_are_inert_and_nan_free(cuda_device):
+    """Rows with ao == 0 (rho == 0 exactly): reverse-mode autodiff of the reference formulas yields NaN there
+    (0 * inf); the kernels return the finite forward-mode derivative, so such rows contribute exactly nothing."""
+    N, n = 3000, 20
+    mol = synthetic_molecule(N, n, n_omega=2, seed=1984, mask_frac=0.02)
+    keep = mol["ao"].abs().sum(dim=1) > 0
+    assert int((~keep).sum()) > 10
+    sub = dict(mol)
+    for k in ("ao", "grad_ao", "grad_n_ao2", "chi", "weights", "coords"):
+        sub[k] = mol[k][keep].contiguous()
+    e_ref, f_ref = oracle.predict_b3lyp(sub)
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    e, f = gd.energy_predictor(gd.B3LYP)(None, m)
+    assert bool(torch.isfinite(f).all())
+    assert abs(float(e) - float(e_ref)) < E_TOL
+    assert relerr(f, f_ref) < F_RTOL
+
+
+def test_free_functions_and_errors(cuda_device):
+    mol = synthetic_molecule(700, 9, n_omega=2, seed=1993)
+    d = {k: (v.to(cuda_device) if isinstance(v, torch.Tensor) else v) for k, v in mol.items()}
+    D = mol["rdm1"]
+    assert relerr(gd.density(d["rdm1"], d["ao"]), oracle.density(D, mol["ao"])) < 1e-11
+    assert relerr(gd.grad_density(d["rdm1"], d["ao"], d["grad_ao"]), oracle.grad_density(D, mol["ao"], mol["grad_ao"])) < 1e-11
+    assert relerr(gd.kinetic_density(d["rdm1"], d["grad_ao"]), oracle.kinetic_density(D, mol["grad_ao"])) < 1e-11
+    assert relerr(gd.lapl_density(d["rdm1"], d["ao"], d["grad_ao"], d["grad_n_ao2"]),
+                  oracle.lapl_density(D, mol["ao"], mol["grad_ao"], mol["grad_n_ao2"])) < 1e-11
+    assert relerr(gd.HF_energy_density(d["rdm1"], d["ao"], d["chi"]), oracle.HF_energy_density(D, mol["ao"], mol["chi"])) < 1e-11
+    P = D.sum(0)
+    assert relerr(gd.coulomb_potential(d["rdm1"].sum(0), d["rep_tensor"]), oracle.coulomb_potential(P, mol["rep_tensor"])) < 1e-11
+    e = gd.nonXC(d["rdm1"].sum(0), d["h1e"], d["rep_tensor"], d["nuclear_repulsion"])
+    assert abs(float(e) - float(oracle.nonXC(P, mol["h1e"], mol["rep_tensor"], mol["nuclear_repulsion"]))) < 1e-9
+    with pytest.raises(TypeError):
+        gd.density(d["rdm1"].float(), d["ao"])
+    with pytest.raises(TypeError):
+        gd.density(d["rdm1"][0], d["ao"])
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    with pytest.raises(ValueError):
+        m.HF_energy_density([0.3])
+    with pytest.raises(ValueError):
+        m.replace(chi=None, omegas=None).HF_energy_density([0.0])
+    occ = m.get_occ()
+    assert torch.equal(occ.cpu(), oracle.get_occ(mol["mo_energy"], mol["mo_occ"].sum(1).round().long()))
+    assert relerr(m.make_rdm1(), oracle.make_rdm1(mol["mo_coeff"], mol["mo_occ"])) < 1e-13
