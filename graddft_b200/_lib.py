@@ -26,6 +26,7 @@ _P = c_void_p
 SIGNATURES = {
     "gdft_version": (c_int, []),
     "gdft_last_cuda_error": (c_int, []),
+    "gdft_launch_count": (ctypes.c_ulonglong, []),
     "gdft_status_string": (c_char_p, [c_int]),
     "gdft_device_supported": (c_int, []),
     "gdft_npad": (c_int64, [c_int64]),

@@ -4,6 +4,7 @@
 namespace gdft {
 
 thread_local int g_last_cuda_error = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -76,6 +77,7 @@ using namespace gdft;
 
 extern "C" int gdft_version(void) { return 100; }
 extern "C" int gdft_last_cuda_error(void) { return g_last_cuda_error; }
+extern "C" unsigned long long gdft_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* gdft_status_string(int s) {
   switch (s) {
     case GDFT_OK: return "ok";

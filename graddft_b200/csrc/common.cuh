@@ -5,11 +5,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include "../../include/gdft_b200.h"
 
 namespace gdft {
 
 extern thread_local int g_last_cuda_error;
+extern std::atomic<unsigned long long> g_launches;  // statistics only: number of kernels launched by this library
 
 inline int cuda_fail(cudaError_t e) {
   g_last_cuda_error = (int)e;
@@ -20,7 +22,12 @@ inline int cuda_fail(cudaError_t e) {
     cudaError_t _e = (expr);                                 \
     if (_e != cudaSuccess) return ::gdft::cuda_fail(_e);     \
   } while (0)
-#define GDFT_LAUNCH_CHECK() GDFT_CUDA_TRY(cudaGetLastError())
+// every kernel launch in the library is followed by this; the counter backs gdft_launch_count()
+#define GDFT_LAUNCH_CHECK()                                  \
+  do {                                                       \
+    ::gdft::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    GDFT_CUDA_TRY(cudaGetLastError());                       \
+  } while (0)
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }

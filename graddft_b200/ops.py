@@ -18,6 +18,27 @@ from ._lib import GDFT_GRAD, GDFT_HF, GDFT_LAPL, GDFT_RHO, GDFT_TAU, check, lib,
 
 F64 = torch.float64
 
+# Optional timing hook (bench.py): when a dict is installed, the named C-ABI calls are bracketed by CUDA events
+# on the launching stream and the (start, end) pairs appended to TIMING[name].  None = no overhead.
+TIMING: Optional[dict] = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if TIMING is not None:
+            self.b.record()
+            TIMING.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
 
 def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
@@ -101,9 +122,10 @@ def _density_fwd_raw(basis: PackedBasis, rdm1: torch.Tensor, flags: int):
     if (flags & GDFT_HF) and basis.chi_packed is None:
         raise ValueError("Precomputed chi tensor has not been loaded.")
     ws = workspace(L.gdft_workspace_bytes(_lib.OP_DENSITY_FWD, N, basis.n, flags, basis.W), dev)
-    check(L.gdft_density_fwd(stream_ptr(), N, basis.n, flags, basis.nplanes, ptr(basis.planes), ptr(rdm1),
-                             ptr(basis.chi_packed) if flags & GDFT_HF else None, basis.W,
-                             ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(ehf), wptr(ws), ws.numel()), "gdft_density_fwd")
+    with _timed("gdft_density_fwd"):
+        check(L.gdft_density_fwd(stream_ptr(), N, basis.n, flags, basis.nplanes, ptr(basis.planes), ptr(rdm1),
+                                 ptr(basis.chi_packed) if flags & GDFT_HF else None, basis.W,
+                                 ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(ehf), wptr(ws), ws.numel()), "gdft_density_fwd")
     return rho, grho, tau, lapl, ehf
 
 
@@ -112,8 +134,10 @@ def _density_bwd_raw(basis: PackedBasis, flags: int, rho_bar, grho_bar, tau_bar,
     N, dev = basis.N, basis.device
     out = torch.empty((2, basis.n, basis.n), dtype=F64, device=dev)
     ws = workspace(L.gdft_workspace_bytes(_lib.OP_DENSITY_BWD, N, basis.n, flags, 0), dev)
-    check(L.gdft_density_bwd(stream_ptr(), N, basis.n, flags, basis.nplanes, ptr(basis.planes), ptr(_c(rho_bar)), ptr(_c(grho_bar)),
-                             ptr(_c(tau_bar)), ptr(_c(lapl_bar)), ptr(out), wptr(ws), ws.numel()), "gdft_density_bwd")
+    rho_bar, grho_bar, tau_bar, lapl_bar = _c(rho_bar), _c(grho_bar), _c(tau_bar), _c(lapl_bar)
+    with _timed("gdft_density_bwd"):
+        check(L.gdft_density_bwd(stream_ptr(), N, basis.n, flags, basis.nplanes, ptr(basis.planes), ptr(rho_bar), ptr(grho_bar),
+                                 ptr(tau_bar), ptr(lapl_bar), ptr(out), wptr(ws), ws.numel()), "gdft_density_bwd")
     return out
 
 
@@ -215,7 +239,8 @@ def _eri_j_raw(P, eri, want_energy=False):
         raise TypeError(f"rep_tensor must be [n,n,n,n] and rdm1 [n,n]; got {tuple(eri.shape)}, {tuple(P.shape)}")
     J = torch.empty((n, n), dtype=F64, device=P.device)
     EJ = torch.empty((1,), dtype=F64, device=P.device) if want_energy else None
-    check(L.gdft_eri_jk(stream_ptr(), n, ptr(eri), ptr(P), ptr(J), None, ptr(EJ), None, 0), "gdft_eri_jk")
+    with _timed("gdft_eri_jk"):
+        check(L.gdft_eri_jk(stream_ptr(), n, ptr(eri), ptr(P), ptr(J), None, ptr(EJ), None, 0), "gdft_eri_jk")
     return J, EJ
 
 

@@ -75,6 +75,8 @@ enum gdft_pointwise_id {
 
 int gdft_version(void);
 int gdft_last_cuda_error(void);
+/* number of CUDA kernels this library has launched in this process so far (statistics for bench.py) */
+unsigned long long gdft_launch_count(void);
 const char* gdft_status_string(int status);
 /* 1 if the current device is compute capability 10.x (the only supported target), else 0 */
 int gdft_device_supported(void);
