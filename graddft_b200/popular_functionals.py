@@ -17,7 +17,7 @@ from .molecule import Molecule
 Array = torch.Tensor
 
 
-def lsda_x_e(rho: Array, clip_cte: float = 1e-30) -> Array:
+def lsda_x_e(rho: Array, clip_cte) -> Array:
     """popular_functionals.py:29-50."""
     return ops.pointwise("LSDA_X", rho, clip=clip_cte)[:, 0]
 

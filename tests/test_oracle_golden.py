@@ -1,0 +1,113 @@
+"""Pins the CPU oracle (oracle/reference_math.py) to the golden vectors under tests/golden/*.npz, which were
+produced by executing the reference's own source files (tests/golden/make_golden.py + jaxshim.py)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+G = Path(__file__).resolve().parent / "golden"
+F64 = torch.float64
+
+
+def load(name):
+    z = np.load(G / name)
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def close(a, b, rtol=1e-12, atol_scale=1e-13):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.equal(torch.isfinite(a), torch.isfinite(b))  # incl. the reference's own NaNs (0 * inf at clipped points)
+    fin = torch.isfinite(b)
+    scale = float(b[fin].abs().max()) if bool(fin.any()) else 0.0
+    err = (a[fin] - b[fin]).abs()
+    assert bool((err <= rtol * b[fin].abs() + atol_scale * scale + 1e-300).all()), float(err.max())
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_molecule_ops(tag):
+    d = load(f"molecule_ops_{tag}.npz")
+    D, ao, gao, g2, chi = d["rdm1"], d["ao"], d["grad_ao"], d["grad_n_ao2"], d["chi"]
+    close(oracle.density(D, ao), d["out_density"])
+    close(oracle.grad_density(D, ao, gao), d["out_grad_density"])
+    close(oracle.lapl_density(D, ao, gao, g2), d["out_lapl_density"])
+    close(oracle.kinetic_density(D, gao), d["out_kinetic_density"])
+    close(oracle.HF_energy_density(D, ao, chi), d["out_HF_energy_density"])
+    P = D.sum(0)
+    close(oracle.coulomb_potential(P, d["rep_tensor"]), d["out_coulomb_potential"])
+    close(oracle.nonXC(P, d["h1e"], d["rep_tensor"], d["nuclear_repulsion"]), d["out_nonXC"])
+    close(oracle.make_rdm1(d["mo_coeff"], d["mo_occ"]), d["out_make_rdm1"])
+    assert torch.equal(oracle.get_occ(d["mo_energy"], d["mo_occ"].sum(1).round().long()), d["out_get_occ"])
+    # VJP of the whole density family w.r.t. rdm1: torch autograd on the restatement AND the closed formula (a10)
+    Dl = D.clone().requires_grad_(True)
+    outs = [oracle.density(Dl, ao), oracle.grad_density(Dl, ao, gao), oracle.kinetic_density(Dl, gao),
+            oracle.lapl_density(Dl, ao, gao, g2), oracle.HF_energy_density(Dl, ao, chi)]
+    (g,) = torch.autograd.grad(sum((o * d[f"cot{i}"]).sum() for i, o in enumerate(outs)), Dl)
+    close(g, d["out_density_family_vjp"], rtol=1e-11, atol_scale=1e-12)
+    formula = oracle.density_vjp_formula(ao, gao, g2.sum(-1), d["cot0"], d["cot1"], d["cot2"], d["cot3"])
+    formula = formula + oracle.HF_fock(chi, d["cot4"], ao).sum(0)
+    close(formula, d["out_density_family_vjp"], rtol=1e-11, atol_scale=1e-12)
+
+
+def test_pointwise():
+    d = load("pointwise.npz")
+    rho, grho, lapl, cot = d["rho"], d["grad_rho"], d["lapl"], d["cot"]
+    cases = {
+        "lsda_x_e": (lambda r, g, l: oracle.lsda_x_e(r), (0,)),
+        "b88_x_e": (lambda r, g, l: oracle.b88_x_e(r, g), (0, 1)),
+        "pw92_c_e": (lambda r, g, l: oracle.pw92_c_e(r), (0,)),
+        "vwn_c_e": (lambda r, g, l: oracle.vwn_c_e(r), (0,)),
+        "lyp_c_e": (lambda r, g, l: oracle.lyp_c_e(r, g, l), (0, 1, 2)),
+    }
+    names = ("rho", "grad_rho", "lapl")
+    for name, (f, argn) in cases.items():
+        leaves = [t.clone().requires_grad_(True) for t in (rho, grho, lapl)]
+        out = f(*leaves)
+        close(out.detach(), d[f"out_{name}"])
+        grads = torch.autograd.grad((out * cot).sum(), [leaves[a] for a in argn])
+        for a, g in zip(argn, grads):
+            close(g, d[f"vjp_{name}_{names[a]}"], rtol=1e-10, atol_scale=1e-12)
+
+
+def test_dm21_features():
+    d = load("dm21_features.npz")
+    D, ao, gao, chi = d["rdm1"], d["ao"], d["grad_ao"], d["chi"]
+    rho, grho, tau = oracle.density(D, ao), oracle.grad_density(D, ao, gao), oracle.kinetic_density(D, gao)
+    close(oracle.dm21_coefficient_inputs(rho, grho, tau), d["out_dm21_coefficient_inputs"])
+    for t in ("LDA", "GGA", "MGGA"):
+        close(oracle.dm21_densities(rho, grho, tau, t), d[f"out_dm21_densities_{t}"])
+        close(oracle.mgga_feature_densities(rho, grho, tau, t), d[f"out_densities_{t}"])
+    ehf = oracle.HF_energy_density(D, ao, chi)
+    close(oracle.dm21_combine_cinputs(oracle.dm21_coefficient_inputs(rho, grho, tau), ehf), d["out_dm21_combine_cinputs"])
+    close(oracle.dm21_combine_densities(oracle.dm21_densities(rho, grho, tau, "LDA"), ehf), d["out_dm21_combine_densities"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_predictor(tag):
+    d = load(f"predictor_{tag}.npz")
+    mol = {k: v for k, v in d.items() if not k.startswith(("energy_", "fock_", "functional_energy_", "densities_"))}
+    for name in ("LSDA", "B88", "VWN", "LYP", "PW92"):
+        e, f = oracle.predict_semilocal(mol, name)
+        assert abs(float(e) - float(d[f"energy_{name}"])) < 1e-10, name
+        assert abs(float(e) - float(d[f"functional_energy_{name}"])) < 1e-10, name
+        close(f, d[f"fock_{name}"], rtol=1e-9, atol_scale=1e-12)
+    e, f = oracle.predict_b3lyp(mol)
+    assert abs(float(e) - float(d["energy_B3LYP"])) < 1e-10
+    close(f, d["fock_B3LYP"], rtol=1e-9, atol_scale=1e-12)
+
+
+def test_predictor_dm21():
+    d = load("predictor_dm21.npz")
+    mol = {k: v for k, v in d.items() if not k.startswith(("energy_", "fock_", "param_", "out_"))}
+    params = {k[len("param_"):]: v for k, v in d.items() if k.startswith("param_")}
+    D, ao, gao, chi = mol["rdm1"], mol["ao"], mol["grad_ao"], mol["chi"]
+    rho, grho, tau = oracle.density(D, ao), oracle.grad_density(D, ao, gao), oracle.kinetic_density(D, gao)
+    ci = oracle.dm21_combine_cinputs(oracle.dm21_coefficient_inputs(rho, grho, tau), oracle.HF_energy_density(D, ao, chi))
+    close(ci, d["out_cinputs"])
+    close(oracle.dm21_mlp(params, ci), d["out_coefficients"], rtol=1e-10, atol_scale=1e-12)
+    e, f = oracle.predict_dm21(mol, params)
+    assert abs(float(e) - float(d["energy_DM21"])) < 1e-10
+    close(f, d["fock_DM21"], rtol=1e-8, atol_scale=1e-11)
