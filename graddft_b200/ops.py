@@ -60,6 +60,8 @@ class PackedBasis:
                  chi: Optional[torch.Tensor] = None):
         L = lib()
         ao = _c(ao)
+        if not ao.is_cuda:
+            raise _lib.GdftError("graddft_b200 kernels need CUDA tensors (there is no CPU path)")
         self.N, self.n = int(ao.shape[0]), int(ao.shape[1])
         self.device = ao.device
         self.npad = int(L.gdft_npad(self.n))

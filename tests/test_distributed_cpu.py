@@ -1,0 +1,67 @@
+"""Host logic of the grid-sharded path on CPU: shard bounds, payload packing, and the one all-reduce per build with
+world_size 2 over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from graddft_b200 import distributed as gdist
+
+
+def test_shard_bounds_cover_and_balance():
+    for N in (1, 127, 128, 129, 34_000, 500_000, 2_000_000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [gdist.shard_bounds(N, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == N
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 128 + 127
+
+
+def test_shard_tensors_and_pack_roundtrip():
+    N, n = 1000, 5
+    mol = {"ao": torch.randn(N, n, dtype=torch.float64), "grad_ao": torch.randn(N, n, 3, dtype=torch.float64),
+           "weights": torch.rand(N, dtype=torch.float64), "coords": torch.randn(N, 3, dtype=torch.float64),
+           "rdm1": torch.randn(2, n, n, dtype=torch.float64)}
+    parts = [gdist.shard_molecule_tensors(mol, r, 3) for r in range(3)]
+    assert torch.equal(torch.cat([p["ao"] for p in parts]), mol["ao"])
+    assert torch.equal(torch.cat([p["weights"] for p in parts]), mol["weights"])
+    assert all(p["rdm1"] is mol["rdm1"] for p in parts)
+    e, v = torch.tensor(-1.5, dtype=torch.float64), torch.randn(2, n, n, dtype=torch.float64)
+    e2, v2 = gdist.unpack_xc(gdist.pack_xc(e, v), v.shape)
+    assert float(e2) == float(e) and torch.equal(v2, v)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 6
+    g = torch.Generator().manual_seed(100 + rank)
+    e = torch.randn((), generator=g, dtype=torch.float64)
+    v = torch.randn(2, n, n, generator=g, dtype=torch.float64)
+    e_sum, v_sum = gdist.allreduce_xc(e, v)
+    q.put((rank, float(e), v.clone(), float(e_sum), v_sum.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_xc_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    e_tot = res[0][1] + res[1][1]
+    v_tot = res[0][2] + res[1][2]
+    for r in res:
+        assert abs(r[3] - e_tot) < 1e-15 and torch.allclose(r[4], v_tot, rtol=0, atol=1e-15)
