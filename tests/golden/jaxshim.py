@@ -48,10 +48,15 @@ class _AtIdx:
         out = self.arr.clone()
         idx = self.idx
         # JAX scatter semantics: out-of-bounds updates are dropped
-        if isinstance(idx, (int,)) and not (-out.shape[0] <= idx < out.shape[0]):
-            return out
+        parts = idx if isinstance(idx, tuple) else (idx,)
+        if len(parts) == 2 and all(isinstance(p, torch.Tensor) for p in parts):  # diag_indices_from
+            out[parts[0], parts[1]] = value
+            return out.as_subclass(JArray)
+        for d, p in enumerate(parts):
+            if isinstance(p, int) and not (-out.shape[d] <= p < out.shape[d]):
+                return out.as_subclass(JArray)
         out[idx] = value
-        return out
+        return out.as_subclass(JArray)
 
 
 class JArray(torch.Tensor):
@@ -65,6 +70,27 @@ class JArray(torch.Tensor):
     @property
     def at(self):
         return _At(self)
+
+    def __getitem__(self, idx):
+        # JAX gather semantics: out-of-bounds integer indices are clamped
+        parts = idx if isinstance(idx, tuple) else (idx,)
+        if any(isinstance(p, int) for p in parts):
+            fixed, d = [], 0
+            for p in parts:
+                if p is None:
+                    fixed.append(p)
+                    continue
+                if p is Ellipsis:
+                    fixed.append(p)
+                    d = self.dim() - (len([q for q in parts[parts.index(p) + 1:] if q is not None]))
+                    continue
+                if isinstance(p, int) and self.dim() > d:
+                    n = self.shape[d]
+                    p = min(max(p, -n), n - 1)
+                fixed.append(p)
+                d += 1
+            idx = tuple(fixed) if isinstance(idx, tuple) else fixed[0]
+        return super().__getitem__(idx)
 
     def astype(self, dt):
         return self.to(dt)
@@ -195,6 +221,18 @@ jnp.dot = lambda a, b: _j(_j(a) @ _j(b))
 jnp.logical_and = lambda a, b: torch.logical_and(torch.as_tensor(a), torch.as_tensor(b))
 jnp.reshape = lambda x, shape: _j(_j(x).reshape(shape))
 jnp.identity = lambda n, dtype=F64: _j(torch.eye(n, dtype=getattr(dtype, "dt", dtype)))
+jnp.inf = float("inf")
+jnp.moveaxis = lambda x, a, b: _j(torch.movedim(_j(x), a, b))
+jnp.vectorize = lambda f, signature=None: f
+jnp.nan_to_num = lambda x: _j(torch.nan_to_num(_j(x)))
+jnp.divide = lambda a, b: _j(torch.as_tensor(a, dtype=F64) / b)
+jnp.multiply = lambda a, b: _j(a * b)
+jnp.diag_indices_from = lambda x: (torch.arange(x.shape[0]), torch.arange(x.shape[0]))
+jnp.less_equal = lambda a, b: a <= b
+jnp.isclose = lambda a, b, **k: torch.isclose(torch.as_tensor(a, dtype=F64), torch.as_tensor(b, dtype=F64), **k)
+jnp.allclose = lambda a, b, **k: bool(torch.allclose(torch.as_tensor(a, dtype=F64), torch.as_tensor(b, dtype=F64), **k))
+jnp.hstack = lambda xs: _j(torch.hstack([_j(x) for x in xs]))
+jnp.any = lambda x: bool(torch.as_tensor(x).any())
 jnp.diag = lambda x: _j(torch.diag(_j(x)))
 jnp.linalg = types.SimpleNamespace(
     norm=lambda x, ord=None: _j(torch.linalg.norm(_j(x))), eigh=lambda x: tuple(_j(t) for t in torch.linalg.eigh(_j(x))),
@@ -274,15 +312,30 @@ class Precision(enum.Enum):
     HIGHEST = 2
 
 
-def fori_loop(lo, hi, body, init):
-    val = init
-    for i in range(int(lo), int(hi)):
-        val = body(i, val)
+def fori_loop(lower, upper, body_fun, init_val):
+    val = init_val
+    for i in range(int(lower), int(upper)):
+        val = body_fun(i, val)
     return val
 
 
-def cond(pred, t, f, operand=None, *args):
-    return t(operand) if bool(pred) else f(operand)
+def cond(pred, t, f, *operands, **kw):
+    if "operand" in kw:
+        operands = (kw["operand"],)
+    return t(*operands) if bool(pred) else f(*operands)
+
+
+class custom_vjp:
+    """forward values only: the golden vectors never differentiate through safe_eigh"""
+
+    def __init__(self, f):
+        self.f = f
+
+    def __call__(self, *a, **k):
+        return self.f(*a, **k)
+
+    def defvjp(self, fwd, bwd):
+        self.fwd, self.bwd = fwd, bwd
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -383,7 +436,7 @@ def install():
     config = types.SimpleNamespace(x64_enabled=True, update=lambda *a, **k: None)
     jax = mod("jax", numpy=jnp, lax=lax, nn=nn_, random=rnd, profiler=prof, scipy=jsp, tree_util=tree_util, jit=jit, vmap=vmap,
               grad=grad, value_and_grad=value_and_grad, config=config, Array=torch.Tensor,
-              custom_vjp=lambda f: f, debug=types.SimpleNamespace(print=lambda *a, **k: None))
+              custom_vjp=custom_vjp, debug=types.SimpleNamespace(print=lambda *a, **k: None))
     jt = mod("jaxtyping", jaxtyped=_identity_decorator)
     for nm in ("Array", "PyTree", "Scalar", "Float", "Int", "Complex", "PRNGKeyArray", "Bool"):
         setattr(jt, nm, type(nm, (_Subscriptable,), {}))
@@ -395,6 +448,7 @@ def install():
     training = mod("flax.training", train_state=ts, checkpoints=None)
     mod("flax", linen=linen, struct=struct, core=core, training=training)
     mod("optax", GradientTransformation=object, OptState=object, apply_updates=None)
+    mod("chex")
     oc = mod("orbax.checkpoint", Checkpointer=object, PyTreeCheckpointer=object)
     mod("orbax", checkpoint=oc)
 
@@ -432,5 +486,16 @@ def install():
         setattr(pkg, nm, getattr(pop, nm))
     train = load("train")
     pkg.energy_predictor = train.energy_predictor
+    # SCF drivers: the eigen-solver and evaluate.py are the reference's; PySCF-only helpers are absent stubs
+    spec = importlib.util.spec_from_file_location("grad_dft.utils.eigenproblem", REF / "grad_dft" / "utils" / "eigenproblem.py")
+    eig = importlib.util.module_from_spec(spec)
+    sys.modules["grad_dft.utils.eigenproblem"] = eig
+    spec.loader.exec_module(eig)
+    utils.safe_fock_solver = eig.safe_fock_solver
+    utils.Optimizer = object
+    iface = mod("grad_dft.interface", pyscf=mod("grad_dft.interface.pyscf", generate_chi_tensor=None, mol_from_Molecule=None, process_mol=None))
+    iface.__path__ = []
+    evaluate = load("evaluate")
+    pkg.diff_scf_loop, pkg.diff_simple_scf_loop = evaluate.diff_scf_loop, evaluate.diff_simple_scf_loop
     pkg.J = _j
     return pkg

@@ -155,6 +155,16 @@ def main():
     d["out_cinputs"] = np_(cin)
     d["out_coefficients"] = np_(dm21.apply({"params": tree}, cin))
     np.savez_compressed(HERE / "predictor_dm21.npz", **d)
+    # ---- 6. jitted SCF loops (evaluate.py:257-352, 917-1038) ------------------------------------------------
+    mol = synthetic_molecule(260, 8, n_omega=0, seed=1993, mask_frac=0.0, with_grad2=False)
+    m = ref_molecule(mol)
+    d = {k: np_(v) for k, v in mol.items()}
+    for name, cycles in (("B88", 4), ("LSDA", 12)):
+        out = gd.diff_scf_loop(getattr(gd, name), cycles=cycles)(None, m)
+        d[f"diis_energy_{name}_{cycles}"], d[f"diis_rdm1_{name}_{cycles}"], d[f"diis_fock_{name}_{cycles}"] = np_(out.energy), np_(out.rdm1), np_(out.fock)
+    out = gd.diff_simple_scf_loop(gd.LSDA, cycles=3, mixing_factor=0.4)(None, m)
+    d["simple_energy_LSDA_3"], d["simple_rdm1_LSDA_3"] = np_(out.energy), np_(out.rdm1)
+    np.savez_compressed(HERE / "scf_loops.npz", **d)
     for p in sorted(HERE.glob("*.npz")):
         print(p.name, p.stat().st_size)
 

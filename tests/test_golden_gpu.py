@@ -110,3 +110,22 @@ def test_predictor_dm21(cuda_device):
     e, f = gd.energy_predictor(fun)(params, m)
     assert abs(float(e) - float(d["energy_DM21"])) < 1e-8
     close(f, d["fock_DM21"], 1e-7)
+
+
+def test_scf_loops(cuda_device):
+    """diff_scf_loop (DIIS) and diff_simple_scf_loop through the public API vs the reference's evaluate.py outputs.
+    tests/integration/molecules/test_predict_B88.py:82-109 asks 1e-6 kcal/mol between the jitted and non-jitted loops."""
+    from graddft_b200.evaluate import diff_scf_loop, diff_simple_scf_loop, make_jitted_scf_loop
+
+    assert make_jitted_scf_loop is diff_scf_loop
+    d = load("scf_loops.npz")
+    m = molecule({k: v for k, v in d.items() if not k.startswith(("diis_", "simple_"))}, cuda_device)
+    tol = 1e-6 / 627.50947
+    for name, cycles in (("B88", 4), ("LSDA", 12)):
+        out = diff_scf_loop(getattr(gd, name), cycles=cycles)(None, m)
+        assert abs(float(out.energy) - float(d[f"diis_energy_{name}_{cycles}"])) < tol, name
+        close(out.rdm1, d[f"diis_rdm1_{name}_{cycles}"], 1e-6, 1e-8)
+        close(out.fock, d[f"diis_fock_{name}_{cycles}"], 1e-6, 1e-8)
+    out = diff_simple_scf_loop(gd.LSDA, cycles=3, mixing_factor=0.4)(None, m)
+    assert abs(float(out.energy) - float(d["simple_energy_LSDA_3"])) < tol
+    close(out.rdm1, d["simple_rdm1_LSDA_3"], 1e-6, 1e-8)

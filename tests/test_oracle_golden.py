@@ -111,3 +111,13 @@ def test_predictor_dm21():
     e, f = oracle.predict_dm21(mol, params)
     assert abs(float(e) - float(d["energy_DM21"])) < 1e-10
     close(f, d["fock_DM21"], rtol=1e-8, atol_scale=1e-11)
+
+
+def test_scf_loops():
+    """diff_scf_loop / JittableDiis / safe_fock_solver restatement vs the reference's own evaluate.py."""
+    d = load("scf_loops.npz")
+    mol = {k: v for k, v in d.items() if not k.startswith(("diis_", "simple_"))}
+    for name, cycles in (("B88", 4), ("LSDA", 12)):
+        e, out = oracle.diff_scf_loop_energy(mol, lambda m: oracle.predict_semilocal(m, name), cycles)
+        assert abs(float(e) - float(d[f"diis_energy_{name}_{cycles}"])) < 1e-8, (name, float(e), float(d[f"diis_energy_{name}_{cycles}"]))
+        close(out["rdm1"], d[f"diis_rdm1_{name}_{cycles}"], rtol=1e-6, atol_scale=1e-8)
