@@ -20,6 +20,7 @@
 // fragment's 4 k-values are consecutive.  Partial tiles go to the workspace and a second kernel adds the
 // K-splits in fixed order (bitwise run-to-run reproducible).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace gdft {
 
@@ -29,39 +30,87 @@ constexpr int BWD_THREADS = 32 * (BWD_MMA_WARPS + 1);
 constexpr int BWD_MAX_SLOTS = 5;
 constexpr int BWD_COEF_W = 16;  // coefficient rows per grid row (planar: W[coef][Npad])
 constexpr int BWD_MAX_STAGES = 6;
+constexpr int BWD_MAX_MT = 5;
 
 struct BwdTerm {
   int a_plane, nq, slot_plane0, per_spin, coef_row0;
 };
 struct BwdParams {
   int64_t N, rows_per_split;
-  int npad, nterms, tiles_b, stages, maxq;
+  int npad, nsub, nterms, tiles_b, stages, maxq;
   BwdTerm terms[4];
   double* part;  // [ksplit][2][npad][npad]
 };
 
-template <int MT, int NQ>
-__device__ __forceinline__ void bwd_stage_mma(double (&acc)[MT][MT][2], const double* __restrict__ sA, const double* __restrict__ sP,
+// One k-tile of one warp: acc[MI][NJ] += A^T (sum_q coef_q * plane_q).  PITCH is the shared-memory row pitch.
+template <int PITCH, int MI, int NJ, int NQ>
+__device__ __forceinline__ void bwd_stage_mma(double (&acc)[MI][NJ][2], const double* __restrict__ sA, const double* __restrict__ sP,
                                               const double* __restrict__ sC) {
-  constexpr int PITCH = 16 * MT + 4, SLOT_ELEMS = BWD_BKR * PITCH;
+  constexpr int SLOT_ELEMS = BWD_BKR * PITCH;
 #pragma unroll
   for (int k4 = 0; k4 < BWD_BKR / 4; k4++) {
     double c[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) c[q] = sC[2 * q * BWD_BKR + k4 * 4];
-    double b[MT];
+    double b[NJ];
 #pragma unroll
-    for (int j = 0; j < MT; j++) {
+    for (int j = 0; j < NJ; j++) {
       double v = 0.0;
 #pragma unroll
       for (int q = 0; q < NQ; q++) v = fma(c[q], sP[q * SLOT_ELEMS + k4 * 4 * PITCH + j * 8], v);
       b[j] = v;
     }
 #pragma unroll
-    for (int i = 0; i < MT; i++) {
+    for (int i = 0; i < MI; i++) {
       const double a = sA[k4 * 4 * PITCH + i * 8];
 #pragma unroll
-      for (int j = 0; j < MT; j++) dmma884(acc[i][j], a, b[j]);
+      for (int j = 0; j < NJ; j++) dmma884(acc[i][j], a, b[j]);
+    }
+  }
+}
+
+struct BwdWarpCtx {
+  const double* sStage;
+  uint64_t *full, *empty;
+  int stage_elems, S, total, ktiles, maxq, spin, lane;
+  int a_off, b_off;  // element offsets of this warp's fragment origin inside the A / plane tiles (t*PITCH + off + g)
+  int a_row, b_col;  // global row / column of the warp tile's (0,0) element (+g / +2t added at the store)
+  int g, t;
+};
+
+// The whole main loop and the partial-tile store of one consumer warp, specialised on its MI x NJ warp tile.
+template <int MT, int MI, int NJ>
+__device__ __forceinline__ void bwd_consumer(const BwdParams& p, const BwdWarpCtx& w) {
+  constexpr int BKR = BWD_BKR, PITCH = 16 * MT + 4, A_ELEMS = BKR * PITCH, SLOT_ELEMS = BKR * PITCH;
+  double acc[MI][NJ][2];
+#pragma unroll
+  for (int i = 0; i < MI; i++)
+#pragma unroll
+    for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int it = 0; it < w.total; it++) {
+    const int st = it % w.S;
+    const BwdTerm Tm = p.terms[it / w.ktiles];
+    const double* stage = w.sStage + (size_t)st * w.stage_elems;
+    mbar_wait(&w.full[st], (it / w.S) & 1);
+    const double* sA = stage + w.a_off;
+    const double* sP = stage + A_ELEMS + (Tm.per_spin ? w.spin * SLOT_ELEMS : 0) + w.b_off;
+    const double* sC = stage + A_ELEMS + w.maxq * SLOT_ELEMS + (Tm.coef_row0 + w.spin) * BKR + w.t;
+    if (Tm.nq == 1) bwd_stage_mma<PITCH, MI, NJ, 1>(acc, sA, sP, sC);
+    else if (Tm.nq == 4) bwd_stage_mma<PITCH, MI, NJ, 4>(acc, sA, sP, sC);
+    else bwd_stage_mma<PITCH, MI, NJ, 5>(acc, sA, sP, sC);
+    __syncwarp();
+    if (w.lane == 0) mbar_arrive(&w.empty[st]);
+  }
+
+  double* out = p.part + ((size_t)blockIdx.y * 2 + w.spin) * p.npad * p.npad;
+#pragma unroll
+  for (int i = 0; i < MI; i++) {
+    const int a = w.a_row + i * 8 + w.g;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const int b = w.b_col + j * 8 + 2 * w.t;
+      *reinterpret_cast<double2*>(out + (size_t)a * p.npad + b) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
   }
 }
@@ -80,8 +129,13 @@ density_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* empty = full + BWD_MAX_STAGES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  // balanced tiling: the npad/8 sub-tiles of each dimension are split over p.tiles_b tiles as evenly as possible
+  // (sizes differ by at most one sub-tile), and each tile's sub-tiles evenly over its two warps
   const int ta = blockIdx.x / p.tiles_b, tb = blockIdx.x - ta * p.tiles_b;
-  const int a0 = ta * T, b0 = tb * T;
+  const int sub_base = p.nsub / p.tiles_b, sub_rem = p.nsub - sub_base * p.tiles_b;
+  const int a_sub0 = ta * sub_base + min(ta, sub_rem), na = sub_base + (ta < sub_rem ? 1 : 0);
+  const int b_sub0 = tb * sub_base + min(tb, sub_rem), nb = sub_base + (tb < sub_rem ? 1 : 0);
+  const int a0 = a_sub0 * 8, b0 = b_sub0 * 8;
   const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
   const int64_t r_end = min(p.N, r_begin + p.rows_per_split);
   const int ktiles = r_end > r_begin ? (int)((r_end - r_begin + BKR - 1) / BKR) : 0;
@@ -118,37 +172,27 @@ density_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 
   // ---- MMA consumers ------------------------------------------------------------------------------
+  // warp tile = mi x nj sub-tiles with mi, nj in {MT, MT-1} (balanced split); each combination runs its own
+  // fully unrolled loop, so ragged matrix sizes cost no predication in the hot loop
   const int wm = warp & 1, wn = warp >> 1, spin = wn >> 1, nhalf = wn & 1;
-  double acc[MT][MT][2];
-#pragma unroll
-  for (int i = 0; i < MT; i++)
-#pragma unroll
-    for (int j = 0; j < MT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  for (int it = 0; it < total; it++) {
-    const int st = it % S;
-    const BwdTerm Tm = p.terms[it / ktiles];
-    const double* stage = sStage + (size_t)st * stage_elems;
-    mbar_wait(&full[st], (it / S) & 1);
-    const double* sA = stage + t * PITCH + wm * 8 * MT + g;
-    const double* sP = stage + A_ELEMS + (Tm.per_spin ? spin * SLOT_ELEMS : 0) + t * PITCH + nhalf * 8 * MT + g;
-    const double* sC = stage + A_ELEMS + p.maxq * SLOT_ELEMS + (Tm.coef_row0 + spin) * BKR + t;
-    if (Tm.nq == 1) bwd_stage_mma<MT, 1>(acc, sA, sP, sC);
-    else if (Tm.nq == 4) bwd_stage_mma<MT, 4>(acc, sA, sP, sC);
-    else bwd_stage_mma<MT, 5>(acc, sA, sP, sC);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
-  }
-
-  // ---- partial tile -> workspace -----------------------------------------------------------------
-  double* out = p.part + ((size_t)blockIdx.y * 2 + spin) * p.npad * p.npad;
-#pragma unroll
-  for (int i = 0; i < MT; i++) {
-    const int a = a0 + wm * 8 * MT + i * 8 + g;
-#pragma unroll
-    for (int j = 0; j < MT; j++) {
-      const int b = b0 + nhalf * 8 * MT + j * 8 + 2 * t;
-      if (a < p.npad && b < p.npad) *reinterpret_cast<double2*>(out + (size_t)a * p.npad + b) = make_double2(acc[i][j][0], acc[i][j][1]);
+  const int mi = wm == 0 ? (na + 1) / 2 : na / 2, row_off = wm == 0 ? 0 : 8 * ((na + 1) / 2);
+  const int nj = nhalf == 0 ? (nb + 1) / 2 : nb / 2, col_off = nhalf == 0 ? 0 : 8 * ((nb + 1) / 2);
+  BwdWarpCtx w;
+  w.sStage = sStage; w.full = full; w.empty = empty;
+  w.stage_elems = stage_elems; w.S = S; w.total = total; w.ktiles = ktiles; w.maxq = p.maxq; w.spin = spin; w.lane = lane;
+  w.a_off = t * PITCH + row_off + g; w.b_off = t * PITCH + col_off + g;
+  w.a_row = a0 + row_off; w.b_col = b0 + col_off; w.g = g; w.t = t;
+  if (mi == MT && nj == MT) bwd_consumer<MT, MT, MT>(p, w);
+  else if (MT > 1 && mi == MT && nj == MT - 1) bwd_consumer<MT, MT, (MT > 1 ? MT - 1 : 1)>(p, w);
+  else if (MT > 1 && mi == MT - 1 && nj == MT) bwd_consumer<MT, (MT > 1 ? MT - 1 : 1), MT>(p, w);
+  else if (MT > 1 && mi == MT - 1 && nj == MT - 1) bwd_consumer<MT, (MT > 1 ? MT - 1 : 1), (MT > 1 ? MT - 1 : 1)>(p, w);
+  else {
+    // empty warp tile (a 1-sub-tile dimension): keep the ring moving
+    for (int it = 0; it < total; it++) {
+      const int st = it % S;
+      mbar_wait(&full[st], (it / S) & 1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
     }
   }
 }
@@ -208,18 +252,29 @@ struct BwdPlan {
 static BwdPlan plan_bwd(int64_t N, int npad, int maxq) {
   BwdPlan pl{};
   const int nsub = npad / 8;
-  // square CTA tiles 16*c per dimension, c from {5,4,3,2,1}: least padded area, mild penalty for small
-  // warp tiles (fewer DMMA per fragment load)
-  int best = 1;
+  // Balanced square tiling: `tc` tiles per dimension whose sizes (in 8-wide sub-tiles) differ by at most one;
+  // a CTA's time goes as ceil(sa/2)*ceil(sb/2) DMMA per k-step (its busiest warp), the kernel template is the
+  // largest ceil(size/2).  eff[] = measured relative DMMA issue efficiency of the MT x MT warp tile (fragment
+  // loads and the in-register combine amortise better over larger tiles).
+  static const double eff[6] = {0.0, 0.30, 0.53, 0.82, 0.93, 1.00};
+  int best_tc = 1, best_mt = 1;
   double best_cost = 1e300;
-  for (int c = 5; c >= 1; c--) {
-    const int tiles = (nsub + 2 * c - 1) / (2 * c);
-    const double cost = (double)(tiles * 2 * c) * (tiles * 2 * c) * (1.0 + 0.06 * (5 - c));
-    if (cost < best_cost) { best_cost = cost; best = c; }
+  for (int tc = (nsub + 2 * BWD_MAX_MT - 1) / (2 * BWD_MAX_MT); tc <= nsub; tc++) {
+    const int base = nsub / tc, rem = nsub - base * tc;
+    const int smax = base + (rem ? 1 : 0);
+    const int mt = (smax + 1) / 2;
+    if (mt > BWD_MAX_MT) continue;
+    const double per_dim = (double)rem * ((base + 2) / 2) + (double)(tc - rem) * ((base + 1) / 2);
+    const double cost = per_dim * per_dim / eff[mt];
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_tc = tc; best_mt = mt; }
   }
-  pl.mt = best;
-  const int T = 16 * best;
-  pl.tiles_a = pl.tiles_b = (npad + T - 1) / T;
+  if (const char* e = getenv("GDFT_BWD_TILES")) {  // tuning override: tiles per dimension
+    int v = atoi(e);
+    if (v >= 1 && v <= nsub && (((nsub + v - 1) / v) + 1) / 2 <= BWD_MAX_MT) { best_tc = v; best_mt = (((nsub + v - 1) / v) + 1) / 2; }
+  }
+  pl.mt = best_mt;
+  const int T = 16 * best_mt;
+  pl.tiles_a = pl.tiles_b = best_tc;
   const int ntiles = pl.tiles_a * pl.tiles_b;
   const int slots = 148;  // one resident CTA per SM
   const int64_t ktiles_total = (N + BWD_BKR - 1) / BWD_BKR;
@@ -283,7 +338,7 @@ static int run_bwd(cudaStream_t stream, int64_t N, int n, int nplanes_a, const d
   if ((rc = make_tmap_3d(&tmW, W, (uint64_t)Npad, BWD_COEF_W, 1, (uint64_t)Npad * 8, (uint64_t)Npad * BWD_COEF_W * 8, BWD_BKR, BWD_COEF_W)))
     return rc;
   BwdParams p{};
-  p.N = N; p.rows_per_split = pl.rows_per_split; p.npad = npad; p.nterms = nterms; p.tiles_b = pl.tiles_b; p.stages = pl.stages;
+  p.N = N; p.rows_per_split = pl.rows_per_split; p.npad = npad; p.nsub = npad / 8; p.nterms = nterms; p.tiles_b = pl.tiles_b; p.stages = pl.stages;
   p.maxq = maxq;
   for (int i = 0; i < nterms; i++) p.terms[i] = terms[i];
   p.part = part;

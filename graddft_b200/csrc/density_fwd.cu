@@ -20,6 +20,7 @@
 // extent) is a legal dense TMA tile.  D is passed transposed (DT[s][b][a]) so the B operand has the
 // same [col][k] shape as A.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace gdft {
 
@@ -219,6 +220,7 @@ density_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 static int pick_nts(int nsub) {
+  if (const char* e = getenv("GDFT_FWD_NTS")) { int v = atoi(e); if (v >= 1 && v <= 5) return v; }  // tuning override
   int best = 1, best_cost = 1 << 30;
   for (int c = 5; c >= 1; c--) {
     int cost = (nsub + c - 1) / c * c;
