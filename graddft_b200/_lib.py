@@ -46,7 +46,13 @@ SIGNATURES = {
     "gdft_pointwise_bwd": (c_int, [_P, c_int64, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gdft_fock_assemble": (c_int, [_P, c_int64, _P, _P, _P, c_double, _P]),
     "gdft_fock_add_sym": (c_int, [_P, c_int64, _P, c_double, _P]),
+    "gdft_xla_last_status": (c_int, []),
+    "gdft_xla_dims_size": (c_size_t, []),
 }
+# XLA custom-call adapters: void(stream, void** buffers, const char* opaque, size_t opaque_len)
+for _name in ("density_fwd", "density_bwd", "hf_fock", "eri_j", "eri_j_transpose", "xc_integrate_fwd", "xc_integrate_bwd",
+              "pointwise_fwd", "pointwise_bwd"):
+    SIGNATURES[f"gdft_{_name}_xla"] = (None, [_P, ctypes.POINTER(_P), c_char_p, c_size_t])
 
 _lib = None
 

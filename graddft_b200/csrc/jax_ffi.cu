@@ -1,0 +1,114 @@
+// XLA custom-call adapters (legacy "API_VERSION_STATUS_RETURNING"-free ABI: void(cudaStream_t, void** buffers,
+// const char* opaque, size_t opaque_len)), so that the kernels can be registered as JAX custom calls with
+// jax.ffi.register_ffi_target(..., api_version=0) / xla_client.register_custom_call_target and wrapped in
+// jax.custom_vjp (graddft_b200/jax_ffi.py).  No XLA headers are needed for this ABI.  `buffers` lists the operands
+// in order, then the results; `opaque` is a packed GdftXlaDims.  Errors cannot be returned through this ABI, so a
+// failing call poisons its first result with NaN (visible downstream) and records the status for
+// gdft_xla_last_status().  Nothing here contains arithmetic.
+//
+// NOTE: JAX is not installed in the build/test environment of this repository, so these adapters are compiled and
+// exported but not exercised by the test-suite; the torch bindings (ops.py) drive the very same C-ABI entry points.
+#include "common.cuh"
+
+namespace gdft {
+struct XlaDims {
+  int64_t N, n, F, c_rows;
+  int32_t flags, nplanes, W, id;
+  double clip;
+  uint64_t ws_bytes;
+};
+thread_local int g_xla_status = 0;
+
+__global__ void poison_kernel(double* p) { *p = __longlong_as_double(0x7ff8000000000000LL); }
+
+static void finish(int rc, cudaStream_t s, void* first_result) {
+  g_xla_status = rc;
+  if (rc != GDFT_OK && first_result) poison_kernel<<<1, 1, 0, s>>>(static_cast<double*>(first_result));
+}
+static bool dims_ok(const char* opaque, size_t len, XlaDims* d) {
+  if (!opaque || len != sizeof(XlaDims)) { g_xla_status = GDFT_BAD_ARGUMENT; return false; }
+  memcpy(d, opaque, sizeof(XlaDims));
+  return true;
+}
+}  // namespace gdft
+using namespace gdft;
+
+extern "C" int gdft_xla_last_status(void) { return g_xla_status; }
+extern "C" size_t gdft_xla_dims_size(void) { return sizeof(XlaDims); }
+
+// operands: packed, rdm1, chi_packed | results: rho, grad_rho, tau, lapl, ehf, ws   (unused ones are 1-element dummies)
+extern "C" void gdft_density_fwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  const int f = d.flags;
+  int rc = gdft_density_fwd(s, d.N, d.n, f, d.nplanes, (const double*)b[0], (const double*)b[1], (f & GDFT_HF) ? (const double*)b[2] : nullptr,
+                            d.W, (f & GDFT_RHO) ? (double*)b[3] : nullptr, (f & GDFT_GRAD) ? (double*)b[4] : nullptr,
+                            (f & GDFT_TAU) ? (double*)b[5] : nullptr, (f & GDFT_LAPL) ? (double*)b[6] : nullptr,
+                            (f & GDFT_HF) ? (double*)b[7] : nullptr, b[8], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[3]);
+}
+// operands: packed, rho_bar, grad_rho_bar, tau_bar, lapl_bar | results: rdm1_bar, ws
+extern "C" void gdft_density_bwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  const int f = d.flags;
+  int rc = gdft_density_bwd(s, d.N, d.n, f, d.nplanes, (const double*)b[0], (f & GDFT_RHO) ? (const double*)b[1] : nullptr,
+                            (f & GDFT_GRAD) ? (const double*)b[2] : nullptr, (f & GDFT_TAU) ? (const double*)b[3] : nullptr,
+                            (f & GDFT_LAPL) ? (const double*)b[4] : nullptr, (double*)b[5], b[6], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[5]);
+}
+// operands: packed, chi_packed, g | results: fock, ws
+extern "C" void gdft_hf_fock_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_hf_fock(s, d.N, d.n, d.W, d.nplanes, (const double*)b[0], (const double*)b[1], (const double*)b[2], (double*)b[3], b[4], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[3]);
+}
+// operands: eri, P | results: J, EJ
+extern "C" void gdft_eri_j_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_eri_jk(s, d.n, (const double*)b[0], (const double*)b[1], (double*)b[2], nullptr, (double*)b[3], nullptr, 0);
+  finish(rc, (cudaStream_t)s, b[2]);
+}
+// operands: eri, Jbar | results: Pbar, ws
+extern "C" void gdft_eri_j_transpose_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_eri_j_transpose(s, d.n, (const double*)b[0], (const double*)b[1], (double*)b[2], b[3], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[2]);
+}
+// operands: c, d, w | results: E, ws
+extern "C" void gdft_xc_integrate_fwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_xc_integrate_fwd(s, d.N, (int)d.F, d.c_rows, (const double*)b[0], (const double*)b[1], (const double*)b[2], d.clip, (double*)b[3],
+                                 b[4], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[3]);
+}
+// operands: c, d, w, E_bar | results: c_bar, d_bar, ws
+extern "C" void gdft_xc_integrate_bwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_xc_integrate_bwd(s, d.N, (int)d.F, d.c_rows, (const double*)b[0], (const double*)b[1], (const double*)b[2], d.clip,
+                                 (const double*)b[3], (double*)b[4], (double*)b[5], b[6], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[5]);
+}
+// operands: rho, grad_rho, tau, lapl | results: out
+extern "C" void gdft_pointwise_fwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_pointwise_fwd(s, d.N, d.id, d.clip, (const double*)b[0], (d.flags & 1) ? (const double*)b[1] : nullptr,
+                              (d.flags & 4) ? (const double*)b[2] : nullptr, (d.flags & 2) ? (const double*)b[3] : nullptr, (double*)b[4]);
+  finish(rc, (cudaStream_t)s, b[4]);
+}
+// operands: rho, grad_rho, tau, lapl, out_bar | results: rho_bar, grad_rho_bar, tau_bar, lapl_bar
+extern "C" void gdft_pointwise_bwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_pointwise_bwd(s, d.N, d.id, d.clip, (const double*)b[0], (d.flags & 1) ? (const double*)b[1] : nullptr,
+                              (d.flags & 4) ? (const double*)b[2] : nullptr, (d.flags & 2) ? (const double*)b[3] : nullptr, (const double*)b[4],
+                              (double*)b[5], (d.flags & 1) ? (double*)b[6] : nullptr, (d.flags & 4) ? (double*)b[7] : nullptr,
+                              (d.flags & 2) ? (double*)b[8] : nullptr);
+  finish(rc, (cudaStream_t)s, b[5]);
+}

@@ -167,6 +167,23 @@ int gdft_fock_assemble(gdft_stream_t stream, int64_t n, const double* h1e, const
 int gdft_fock_add_sym(gdft_stream_t stream, int64_t n, const double* V /*[2,n,n]*/, double clip,
                       double* fock /*[2,n,n]*/);
 
+/* ---- XLA custom-call adapters (graddft_b200/csrc/jax_ffi.cu) --------------------------------------
+ * Legacy custom-call ABI void(cudaStream_t, void** buffers, const char* opaque, size_t opaque_len): operands
+ * then results in `buffers`, a packed dims struct (gdft_xla_dims_size() bytes; layout in jax_ffi.py) in `opaque`.
+ * These let jax.ffi / xla_client register the kernels as JAX custom calls (north-star binding); they forward to
+ * the entry points above and contain no arithmetic. */
+int gdft_xla_last_status(void);
+size_t gdft_xla_dims_size(void);
+void gdft_density_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_density_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_hf_fock_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_eri_j_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_eri_j_transpose_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_xc_integrate_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_xc_integrate_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_pointwise_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_pointwise_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+
 #ifdef __cplusplus
 }
 #endif

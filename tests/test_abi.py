@@ -54,3 +54,10 @@ def test_ops_refuse_cpu_tensors():
 
     with pytest.raises(_lib.GdftError):
         ops.PackedBasis(torch.zeros(4, 3, dtype=torch.float64))
+
+
+def test_xla_adapter_dims_layout():
+    from graddft_b200 import jax_ffi
+
+    jax_ffi.check_layout()
+    assert len(jax_ffi.pack_dims(N=5, n=3)) == _lib.lib().gdft_xla_dims_size()
