@@ -231,7 +231,12 @@ def run_ours(args, wl):
         sampler.start()
     launches0 = ops.lib().gdft_launch_count()
     ops.TIMING = {}
+    profile_range = os.environ.get("GDFT_BENCH_PROFILE_RANGE") == "1"  # ncu --profile-from-start off: only the timed steps
+    if profile_range:
+        torch.cuda.profiler.start()
     ms_total = timed(step_resident, args.steps)
+    if profile_range:
+        torch.cuda.profiler.stop()
     timing, ops.TIMING = ops.TIMING, None
     launches = (ops.lib().gdft_launch_count() - launches0) / args.steps
     for _ in range(2):
@@ -252,6 +257,10 @@ def run_ours(args, wl):
         flop_half = 4.0 * Nloc * n * n  # 2 GEMM units per call (both spins): 2 * (2 N n^2)
         ach_bwd = flop_half / bwd_ms / 1e9
         ach_fwd = flop_half / fwd_ms / 1e9
+        traffic = None
+        tpath = ROOT / "profiles" / "r1_traffic.json"
+        if world == 1 and tpath.exists():  # dram bytes per launch from the committed ncu --set full capture of this workload
+            traffic = json.loads(tpath.read_text()).get(args.workload, {}).get("density_bwd_kernel")
         value = args.steps / (ms_total / 1e3)
         e2e = args.steps / (ms_e2e / 1e3)
         cpu_rate, cores, cpu_dt = (None, None, None)
@@ -273,7 +282,7 @@ def run_ours(args, wl):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "density_bwd_kernel (gdft_density_bwd: aoT.M split-K DMMA GEMM)",
-                         "achieved": ach_bwd, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": ach_bwd / dgemm_tf, "traffic": None,
+                         "achieved": ach_bwd, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": ach_bwd / dgemm_tf, "traffic": traffic,
                          "flop_per_launch": flop_half, "ms_per_launch": bwd_ms,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json carries no FP64 figure); 'of measured'"},
             "roofline_fwd": {"bound": "tensor", "kernel": "density_fwd_kernel (gdft_density_fwd: ao.D DMMA GEMM + fused row dots)",
