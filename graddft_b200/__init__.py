@@ -13,7 +13,7 @@ from .functional import (  # noqa: F401
     dm21_densities, dm21_hfgrads_cinputs, dm21_hfgrads_densities, stop_gradient,
 )
 from .popular_functionals import B3LYP, B88, LSDA, LYP, PW92, VWN  # noqa: F401
-from .train import energy_predictor, molecule_predictor, xc_energy_and_grads  # noqa: F401
+from .train import energy_predictor, molecule_predictor, mse_energy_loss, simple_energy_loss, train_kernel, xc_energy_and_grads  # noqa: F401
 from .evaluate import (  # noqa: F401
-    JittableDiis, diff_scf_loop, diff_simple_scf_loop, make_jitted_scf_loop, make_simple_scf_loop, safe_eigh, safe_fock_solver,
+    JittableDiis, non_scf_predictor, diff_scf_loop, diff_simple_scf_loop, make_jitted_scf_loop, make_simple_scf_loop, safe_eigh, safe_fock_solver,
 )

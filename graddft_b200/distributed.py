@@ -60,3 +60,34 @@ def allreduce_xc(exc: torch.Tensor, vxc: torch.Tensor, group=None, buf: Optional
     buf = pack_xc(exc, vxc, buf)
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return unpack_xc(buf, vxc.shape)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# molecule (batch) sharding: independent molecules of a training batch, one gradient all-reduce per step
+# (the reference loops serially, grad_dft/train.py:493-494,519-528)
+# ---------------------------------------------------------------------------------------------------------
+def shard_molecules(costs, rank: int, world: int):
+    """Indices of the molecules rank `rank` evaluates: longest-processing-time-first greedy balance on the given
+    per-molecule costs (N_i * n_i^2), deterministic, identical on every rank."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * world
+    mine = []
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += costs[i]
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+def allreduce_gradients(grads, loss: Optional[torch.Tensor] = None, group=None):
+    """Sum parameter gradients (and the loss) over the molecule shards with ONE collective on a flat buffer."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return grads, loss
+    flat = torch.cat([g.reshape(-1) for g in grads] + ([loss.reshape(1)] if loss is not None else []))
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    out, off = [], 0
+    for g in grads:
+        out.append(flat[off:off + g.numel()].reshape(g.shape))
+        off += g.numel()
+    return out, (flat[off] if loss is not None else None)

@@ -118,6 +118,17 @@ class JittableDiis:
         return torch.einsum("ji,sjk,kl->sil", self.A, F, self.A), diis_data
 
 
+def non_scf_predictor(functional: Functional, chunk_size: int = 1024, **kwargs) -> Callable:
+    """grad_dft/evaluate.py:88-126: one predictor call; returns the molecule with `.fock` and `.energy` set."""
+    compute_energy = energy_predictor(functional, **kwargs)
+
+    def predictor(params, atoms: Molecule, *args) -> Molecule:
+        predicted_e, fock = compute_energy(params, atoms, *args)
+        return atoms.replace(fock=fock, energy=predicted_e)
+
+    return predictor
+
+
 def _scf_body(compute_energy, params, molecule: Molecule, fock: Array, *args) -> Tuple[Molecule, Array]:
     """Diagonalise, re-occupy, rebuild rdm1, predict  (evaluate.py:996-1016)."""
     mo_energy, mo_coeff = safe_fock_solver(fock, molecule.s1e)

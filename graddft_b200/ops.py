@@ -12,6 +12,7 @@ from typing import Optional, Tuple
 
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 from ._lib import GDFT_GRAD, GDFT_HF, GDFT_LAPL, GDFT_RHO, GDFT_TAU, check, lib, ptr, stream_ptr, workspace, wptr
@@ -368,6 +369,7 @@ class _Pointwise(Function):
         return out
 
     @staticmethod
+    @once_differentiable  # the per-point VJP kernel is first-order: differentiating through it raises instead of silently dropping terms
     def backward(ctx, out_bar):
         L = lib()
         saved = list(ctx.saved_tensors)

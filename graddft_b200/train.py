@@ -34,17 +34,18 @@ def xc_energy_and_grads(functional: Functional, params, rdm1: Array, atoms: Mole
     """value_and_grad(argnums=1) of the XC energy (grad_dft/train.py:86-121): one "XC build" = forward
     (densities -> features -> E_xc) + VJP (-> V_xc [2,n,n], un-symmetrised).  Also returns the molecule
     carrying the differentiated rdm1 (its cached grid quantities are reused by the hybrid terms)."""
+    keep_exc_graph = torch.is_grad_enabled() and (_requires_grad(params) or rdm1.requires_grad)
     if create_graph is None:
-        create_graph = torch.is_grad_enabled() and (_requires_grad(params) or rdm1.requires_grad)
+        create_graph = False  # V_xc differentiable w.r.t. params/rdm1 needs second-order per-point kernels (not bound yet)
     leaf = rdm1 if (create_graph and rdm1.requires_grad) else rdm1.detach().requires_grad_(True)
     with torch.enable_grad():
         at = atoms.replace(rdm1=leaf)
         densities = functional.compute_densities(at, *args, **functional_kwargs)
         cinputs = functional.compute_coefficient_inputs(at, *args)
         exc = functional.xc_energy(params, at.grid, cinputs, densities, **functional_kwargs)
-        (fock_xc,) = torch.autograd.grad(exc, leaf, create_graph=create_graph)
-    if not create_graph:
-        exc = exc.detach()
+        (fock_xc,) = torch.autograd.grad(exc, leaf, create_graph=create_graph, retain_graph=keep_exc_graph or create_graph)
+    if not (keep_exc_graph or create_graph):
+        exc = exc.detach()  # otherwise E_xc stays differentiable w.r.t. params (first order: energy losses, train.py:312-359)
     return exc, fock_xc, at
 
 
@@ -55,7 +56,7 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
 
     def predict(params, atoms: Molecule, *args) -> Tuple[Array, Array]:
         exc, fock_xc, at = xc_energy_and_grads(functional, params, atoms.rdm1, atoms, *args)
-        differentiable = exc.requires_grad
+        differentiable = fock_xc.requires_grad
         P = atoms.rdm1.sum(dim=0)
         if differentiable or atoms.rdm1.requires_grad:
             J = ops.coulomb_j(P, atoms.rep_tensor)
@@ -123,3 +124,64 @@ def _add_sym(fock: Array, v: Array, clip_cte: float) -> Array:
 
 
 molecule_predictor = energy_predictor  # name used in the notebooks' prose
+
+
+# ---------------------------------------------------------------------------------------------------------
+# losses and the training kernel  (grad_dft/train.py:312-359, 480-575; thin scalar glue over the predictor)
+# ---------------------------------------------------------------------------------------------------------
+def mse_energy_loss(params, compute_energy: Callable, atoms_list, truth_energies, elec_num_norm: bool = True, ranks=None) -> Array:
+    """grad_dft/train.py:480-535: mean over molecules of ((E_pred - E_true) / n_elec)^2.  `compute_energy` is a
+    non-SCF or SCF predictor returning a Molecule with `.energy`.  With `ranks=(rank, world)` only the molecules
+    assigned to this rank (`distributed.shard_molecules`) are evaluated and the caller all-reduces loss and gradients
+    (`distributed.allreduce_gradients`): the reference loops serially over the batch (train.py:519)."""
+    if isinstance(atoms_list, Molecule):
+        atoms_list = [atoms_list]
+    idx = range(len(atoms_list))
+    if ranks is not None:
+        from .distributed import shard_molecules
+        idx = shard_molecules([m.grid_size * m.ao.shape[1] ** 2 for m in atoms_list], *ranks)
+    total = 0.0
+    for i in idx:
+        atoms = atoms_list[i]
+        out = compute_energy(params, atoms)
+        diff = out.energy - truth_energies[i]
+        if elec_num_norm:
+            num_elec = atoms.mo_occ.sum() if atoms.atom_index is None else (torch.as_tensor(atoms.atom_index).sum() - atoms.charge)
+            diff = diff / num_elec
+        total = total + diff ** 2
+    return total / len(atoms_list)
+
+
+def simple_energy_loss(params, compute_energy: Callable, atoms: Molecule, truth_energy):
+    """grad_dft/train.py:537-560 (value_and_grad, has_aux): ((loss, E_pred), grads w.r.t. params)."""
+    leaves = [p for p in _leaves(params) if p.requires_grad]
+    out = compute_energy(params, atoms)
+    loss = (out.energy - truth_energy) ** 2
+    grads = torch.autograd.grad(loss, leaves)
+    return (loss.detach(), out.energy.detach()), grads
+
+
+def _leaves(params):
+    if isinstance(params, torch.Tensor):
+        return [params]
+    if isinstance(params, dict):
+        return [l for v in params.values() for l in _leaves(v)]
+    if isinstance(params, (list, tuple)):
+        return [l for v in params for l in _leaves(v)]
+    return []
+
+
+def train_kernel(tx: "torch.optim.Optimizer", loss: Callable) -> Callable:
+    """grad_dft/train.py:312-359 with a torch optimizer standing in for the optax GradientTransformation:
+    kernel(params, atoms, truth) -> (params, loss, predicted_energy); the optimizer holds the state."""
+
+    def kernel(params, atoms, ground_truth_energy, *args):
+        (cost_value, predicted), grads = loss(params, atoms, ground_truth_energy)
+        leaves = [p for p in _leaves(params) if p.requires_grad]
+        for p, g in zip(leaves, grads):
+            p.grad = g
+        tx.step()
+        tx.zero_grad(set_to_none=True)
+        return params, cost_value, predicted
+
+    return kernel

@@ -65,3 +65,43 @@ def test_allreduce_xc_world2_gloo():
     v_tot = res[0][2] + res[1][2]
     for r in res:
         assert abs(r[3] - e_tot) < 1e-15 and torch.allclose(r[4], v_tot, rtol=0, atol=1e-15)
+
+
+def test_shard_molecules_balanced_and_complete():
+    g = torch.Generator().manual_seed(1993)
+    costs = [float((1e4 * (1 + 3 * torch.rand((), generator=g))) * (12 + int(88 * torch.rand((), generator=g))) ** 2) for _ in range(64)]
+    for world in (1, 2, 4, 8):
+        parts = [gdist.shard_molecules(costs, r, world) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(64))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) <= 1.15 * (sum(costs) / world)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7 + rank)
+    grads = [torch.randn(3, 4, generator=g, dtype=torch.float64), torch.randn(5, generator=g, dtype=torch.float64)]
+    loss = torch.randn((), generator=g, dtype=torch.float64)
+    out, l = gdist.allreduce_gradients(grads, loss)
+    q.put((rank, [x.clone() for x in grads], float(loss), [x.clone() for x in out], float(l)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for k in range(2):
+        tot = res[0][1][k] + res[1][1][k]
+        assert torch.allclose(res[0][3][k], tot, rtol=0, atol=1e-15) and torch.allclose(res[1][3][k], tot, rtol=0, atol=1e-15)
+    assert abs(res[0][4] - (res[0][2] + res[1][2])) < 1e-15
