@@ -42,65 +42,99 @@ struct BwdParams {
   double* part;  // [ksplit][2][npad][npad]
 };
 
-// One k-tile of one warp: acc[MI][NJ] += A^T (sum_q coef_q * plane_q).  PITCH is the shared-memory row pitch.
+// Fragments of one 4-row k-step of one warp: a[i] = A[k][i*8+g], b[j] = sum_q coef_q[k] * plane_q[k][j*8+g]
+// (k = k4*4 + t).  PITCH is the shared-memory row pitch.
 template <int PITCH, int MI, int NJ, int NQ>
-__device__ __forceinline__ void bwd_stage_mma(double (&acc)[MI][NJ][2], const double* __restrict__ sA, const double* __restrict__ sP,
-                                              const double* __restrict__ sC) {
+__device__ __forceinline__ void bwd_load_frags(double (&a)[MI], double (&b)[NJ], const double* __restrict__ sA,
+                                               const double* __restrict__ sP, const double* __restrict__ sC, int k4) {
   constexpr int SLOT_ELEMS = BWD_BKR * PITCH;
+  double c[NQ];
 #pragma unroll
-  for (int k4 = 0; k4 < BWD_BKR / 4; k4++) {
-    double c[NQ];
+  for (int q = 0; q < NQ; q++) c[q] = sC[2 * q * BWD_BKR + k4 * 4];
 #pragma unroll
-    for (int q = 0; q < NQ; q++) c[q] = sC[2 * q * BWD_BKR + k4 * 4];
-    double b[NJ];
+  for (int j = 0; j < NJ; j++) {
+    double v = c[0] * sP[k4 * 4 * PITCH + j * 8];
 #pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      double v = 0.0;
-#pragma unroll
-      for (int q = 0; q < NQ; q++) v = fma(c[q], sP[q * SLOT_ELEMS + k4 * 4 * PITCH + j * 8], v);
-      b[j] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < MI; i++) {
-      const double a = sA[k4 * 4 * PITCH + i * 8];
-#pragma unroll
-      for (int j = 0; j < NJ; j++) dmma884(acc[i][j], a, b[j]);
-    }
+    for (int q = 1; q < NQ; q++) v = fma(c[q], sP[q * SLOT_ELEMS + k4 * 4 * PITCH + j * 8], v);
+    b[j] = v;
   }
+#pragma unroll
+  for (int i = 0; i < MI; i++) a[i] = sA[k4 * 4 * PITCH + i * 8];
+}
+
+template <int MI, int NJ>
+__device__ __forceinline__ void bwd_mma_step(double (&acc)[MI][NJ][2], const double (&a)[MI], const double (&b)[NJ]) {
+#pragma unroll
+  for (int i = 0; i < MI; i++)
+#pragma unroll
+    for (int j = 0; j < NJ; j++) dmma884(acc[i][j], a[i], b[j]);
 }
 
 struct BwdWarpCtx {
   const double* sStage;
   uint64_t *full, *empty;
-  int stage_elems, S, total, ktiles, maxq, spin, lane;
+  int stage_elems, S, ktiles, maxq, spin, lane;
   int a_off, b_off;  // element offsets of this warp's fragment origin inside the A / plane tiles (t*PITCH + off + g)
   int a_row, b_col;  // global row / column of the warp tile's (0,0) element (+g / +2t added at the store)
   int g, t;
 };
 
+// One term (ktiles k-tiles starting at ring position st/ph) of one consumer warp, software-pipelined over the
+// flattened 4-row k-steps: the fragments of step k+1 (LDS + the in-register combine) are issued before the DMMAs
+// of step k, and at a stage boundary the wait on the next stage's full barrier and its first fragment loads are
+// hoisted above the last DMMA block of the current stage, so the DMMA stream of a warp never drains between stages.
+template <int PITCH, int MI, int NJ, int NQ>
+__device__ __forceinline__ void bwd_term_loop(double (&acc)[MI][NJ][2], const BwdWarpCtx& w, const BwdTerm& Tm, int& st, uint32_t& ph) {
+  constexpr int BKR = BWD_BKR, A_ELEMS = BKR * PITCH, SLOT_ELEMS = BKR * PITCH;
+  const int p_off = A_ELEMS + (Tm.per_spin ? w.spin * SLOT_ELEMS : 0) + w.b_off;
+  const int c_off = A_ELEMS + w.maxq * SLOT_ELEMS + (Tm.coef_row0 + w.spin) * BKR + w.t;
+  double a[2][MI], b[2][NJ];
+  const double* stage = w.sStage + (size_t)st * w.stage_elems;
+  mbar_wait(&w.full[st], ph);
+  bwd_load_frags<PITCH, MI, NJ, NQ>(a[0], b[0], stage + w.a_off, stage + p_off, stage + c_off, 0);
+  for (int kt = 0; kt < w.ktiles; kt++) {
+    const double* sA = stage + w.a_off;
+    const double* sP = stage + p_off;
+    const double* sC = stage + c_off;
+    const int st_cur = st;
+    bwd_load_frags<PITCH, MI, NJ, NQ>(a[1], b[1], sA, sP, sC, 1);
+    bwd_mma_step<MI, NJ>(acc, a[0], b[0]);
+    bwd_load_frags<PITCH, MI, NJ, NQ>(a[0], b[0], sA, sP, sC, 2);
+    bwd_mma_step<MI, NJ>(acc, a[1], b[1]);
+    bwd_load_frags<PITCH, MI, NJ, NQ>(a[1], b[1], sA, sP, sC, 3);
+    bwd_mma_step<MI, NJ>(acc, a[0], b[0]);
+    // advance the ring; prefetch the first fragments of the next stage of this term
+    if (++st == w.S) { st = 0; ph ^= 1u; }
+    stage = w.sStage + (size_t)st * w.stage_elems;
+    if (kt + 1 < w.ktiles) {
+      mbar_wait(&w.full[st], ph);
+      bwd_load_frags<PITCH, MI, NJ, NQ>(a[0], b[0], stage + w.a_off, stage + p_off, stage + c_off, 0);
+    }
+    bwd_mma_step<MI, NJ>(acc, a[1], b[1]);
+    __syncwarp();
+    if (w.lane == 0) mbar_arrive(&w.empty[st_cur]);
+  }
+}
+
 // The whole main loop and the partial-tile store of one consumer warp, specialised on its MI x NJ warp tile.
 template <int MT, int MI, int NJ>
 __device__ __forceinline__ void bwd_consumer(const BwdParams& p, const BwdWarpCtx& w) {
-  constexpr int BKR = BWD_BKR, PITCH = 16 * MT + 4, A_ELEMS = BKR * PITCH, SLOT_ELEMS = BKR * PITCH;
+  constexpr int PITCH = 16 * MT + 4;
   double acc[MI][NJ][2];
 #pragma unroll
   for (int i = 0; i < MI; i++)
 #pragma unroll
     for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int it = 0; it < w.total; it++) {
-    const int st = it % w.S;
-    const BwdTerm Tm = p.terms[it / w.ktiles];
-    const double* stage = w.sStage + (size_t)st * w.stage_elems;
-    mbar_wait(&w.full[st], (it / w.S) & 1);
-    const double* sA = stage + w.a_off;
-    const double* sP = stage + A_ELEMS + (Tm.per_spin ? w.spin * SLOT_ELEMS : 0) + w.b_off;
-    const double* sC = stage + A_ELEMS + w.maxq * SLOT_ELEMS + (Tm.coef_row0 + w.spin) * BKR + w.t;
-    if (Tm.nq == 1) bwd_stage_mma<PITCH, MI, NJ, 1>(acc, sA, sP, sC);
-    else if (Tm.nq == 4) bwd_stage_mma<PITCH, MI, NJ, 4>(acc, sA, sP, sC);
-    else bwd_stage_mma<PITCH, MI, NJ, 5>(acc, sA, sP, sC);
-    __syncwarp();
-    if (w.lane == 0) mbar_arrive(&w.empty[st]);
+  int st = 0;
+  uint32_t ph = 0;
+  if (w.ktiles > 0) {
+    for (int term = 0; term < p.nterms; term++) {
+      const BwdTerm Tm = p.terms[term];
+      if (Tm.nq == 1) bwd_term_loop<PITCH, MI, NJ, 1>(acc, w, Tm, st, ph);
+      else if (Tm.nq == 4) bwd_term_loop<PITCH, MI, NJ, 4>(acc, w, Tm, st, ph);
+      else bwd_term_loop<PITCH, MI, NJ, 5>(acc, w, Tm, st, ph);
+    }
   }
 
   double* out = p.part + ((size_t)blockIdx.y * 2 + w.spin) * p.npad * p.npad;
@@ -179,7 +213,7 @@ density_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int nj = nhalf == 0 ? (nb + 1) / 2 : nb / 2, col_off = nhalf == 0 ? 0 : 8 * ((nb + 1) / 2);
   BwdWarpCtx w;
   w.sStage = sStage; w.full = full; w.empty = empty;
-  w.stage_elems = stage_elems; w.S = S; w.total = total; w.ktiles = ktiles; w.maxq = p.maxq; w.spin = spin; w.lane = lane;
+  w.stage_elems = stage_elems; w.S = S; w.ktiles = ktiles; w.maxq = p.maxq; w.spin = spin; w.lane = lane;
   w.a_off = t * PITCH + row_off + g; w.b_off = t * PITCH + col_off + g;
   w.a_row = a0 + row_off; w.b_col = b0 + col_off; w.g = g; w.t = t;
   if (mi == MT && nj == MT) bwd_consumer<MT, MT, MT>(p, w);
