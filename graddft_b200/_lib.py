@@ -39,6 +39,8 @@ SIGNATURES = {
     "gdft_hf_fock": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_eri_jk": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_eri_j_transpose": (c_int, [_P, c_int64, _P, _P, _P, _P, c_size_t]),
+    "gdft_eri_j_rows": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
+    "gdft_eri_j_transpose_rows": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, c_size_t]),
     "gdft_xc_integrate_fwd": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P, c_double, _P, _P, c_size_t]),
     "gdft_xc_integrate_bwd": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P, c_double, _P, _P, _P, _P, c_size_t]),
     "gdft_pointwise_ncols": (c_int, [c_int]),

@@ -266,19 +266,27 @@ __global__ void fock_add_sym_kernel(int n, const double* __restrict__ V, double 
 
 using namespace gdft;
 
+// Row block [row0, row0+rows) of the (pq) x (rt) sweep: `eri_rows` points at the block's first row.  The per-row
+// summation order does not depend on the blocking, so a row-sharded J is bitwise equal to the unsharded one.
+static int eri_j_rows_launch(cudaStream_t stream, int64_t n, int64_t rows, const double* eri_rows, const double* P, double* J_rows) {
+  const int64_t C = n * n;
+  const bool vec = (C % 2 == 0) && aligned16(eri_rows);
+  const int64_t nblocks = (rows + ERI_ROWS_PER_CTA - 1) / ERI_ROWS_PER_CTA;
+  const unsigned grid = (unsigned)imin64(nblocks, 148 * 8);
+  if (vec) eri_j_kernel<true><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
+  else eri_j_kernel<false><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
 extern "C" int gdft_eri_jk(gdft_stream_t stream_, int64_t n, const double* eri, const double* P, double* J, double* K,
                            double* EJ, void* ws, size_t ws_bytes) {
   (void)ws; (void)ws_bytes;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n <= 0 || n > 2048) return GDFT_BAD_SHAPE;
   if (!eri || !P || !J) return GDFT_BAD_ARGUMENT;
-  const int64_t R = n * n, C = n * n;
-  const bool vec = (C % 2 == 0) && aligned16(eri);
-  const int64_t nblocks = (R + ERI_ROWS_PER_CTA - 1) / ERI_ROWS_PER_CTA;
-  const unsigned grid = (unsigned)imin64(nblocks, 148 * 8);
-  if (vec) eri_j_kernel<true><<<grid, ERI_THREADS, 0, stream>>>(R, C, eri, P, J);
-  else eri_j_kernel<false><<<grid, ERI_THREADS, 0, stream>>>(R, C, eri, P, J);
-  GDFT_LAUNCH_CHECK();
+  const int64_t R = n * n;
+  if (int rc = eri_j_rows_launch(stream, n, R, eri, P, J)) return rc;
   if (K) {
     dim3 g((unsigned)n, (unsigned)((n + 7) / 8));
     eri_k_kernel<<<g, 256, 0, stream>>>((int)n, eri, P, K);
@@ -291,6 +299,32 @@ extern "C" int gdft_eri_jk(gdft_stream_t stream_, int64_t n, const double* eri, 
   return GDFT_OK;
 }
 
+extern "C" int gdft_eri_j_rows(gdft_stream_t stream_, int64_t n, int64_t rows, const double* eri_rows, const double* P,
+                               double* J_rows) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || n > 2048 || rows < 0 || rows > n * n) return GDFT_BAD_SHAPE;
+  if (rows == 0) return GDFT_OK;
+  if (!eri_rows || !P || !J_rows) return GDFT_BAD_ARGUMENT;
+  return eri_j_rows_launch(stream, n, rows, eri_rows, P, J_rows);
+}
+
+static int eri_jt_rows_launch(cudaStream_t stream, int64_t n, int64_t rows, const double* eri_rows, const double* Jbar_rows,
+                              double* Pbar, void* ws) {
+  const int64_t R = rows, C = n * n;
+  const bool vec = (C % 2 == 0) && aligned16(eri_rows);
+  int splits = (int)imin64(64, imax64(1, R / 64));
+  const int64_t rows_per_split = (R + splits - 1) / splits;
+  double* part = static_cast<double*>(ws);
+  const int64_t cols_per_cta = vec ? 2 * ERIT_THREADS : ERIT_THREADS;
+  dim3 grid((unsigned)((C + cols_per_cta - 1) / cols_per_cta), (unsigned)splits);
+  if (vec) eri_jt_kernel<true><<<grid, ERIT_THREADS, 0, stream>>>(R, C, rows_per_split, eri_rows, Jbar_rows, part);
+  else eri_jt_kernel<false><<<grid, ERIT_THREADS, 0, stream>>>(R, C, rows_per_split, eri_rows, Jbar_rows, part);
+  GDFT_LAUNCH_CHECK();
+  sum_splits_kernel<<<(unsigned)((C + 255) / 256), 256, 0, stream>>>(C, splits, part, Pbar);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
 extern "C" int gdft_eri_j_transpose(gdft_stream_t stream_, int64_t n, const double* eri, const double* Jbar, double* Pbar,
                                     void* ws, size_t ws_bytes) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -298,19 +332,17 @@ extern "C" int gdft_eri_j_transpose(gdft_stream_t stream_, int64_t n, const doub
   if (!eri || !Jbar || !Pbar) return GDFT_BAD_ARGUMENT;
   if (!aligned16(ws)) return GDFT_BAD_ALIGNMENT;
   if (ws_bytes < eri_workspace(n)) return GDFT_WORKSPACE_TOO_SMALL;
-  const int64_t R = n * n, C = n * n;
-  const bool vec = (C % 2 == 0) && aligned16(eri);
-  int splits = (int)imin64(64, imax64(1, R / 64));
-  const int64_t rows_per_split = (R + splits - 1) / splits;
-  double* part = static_cast<double*>(ws);
-  const int64_t cols_per_cta = vec ? 2 * ERIT_THREADS : ERIT_THREADS;
-  dim3 grid((unsigned)((C + cols_per_cta - 1) / cols_per_cta), (unsigned)splits);
-  if (vec) eri_jt_kernel<true><<<grid, ERIT_THREADS, 0, stream>>>(R, C, rows_per_split, eri, Jbar, part);
-  else eri_jt_kernel<false><<<grid, ERIT_THREADS, 0, stream>>>(R, C, rows_per_split, eri, Jbar, part);
-  GDFT_LAUNCH_CHECK();
-  sum_splits_kernel<<<(unsigned)((C + 255) / 256), 256, 0, stream>>>(C, splits, part, Pbar);
-  GDFT_LAUNCH_CHECK();
-  return GDFT_OK;
+  return eri_jt_rows_launch(stream, n, n * n, eri, Jbar, Pbar, ws);
+}
+
+extern "C" int gdft_eri_j_transpose_rows(gdft_stream_t stream_, int64_t n, int64_t rows, const double* eri_rows,
+                                         const double* Jbar_rows, double* Pbar, void* ws, size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || n > 2048 || rows <= 0 || rows > n * n) return GDFT_BAD_SHAPE;
+  if (!eri_rows || !Jbar_rows || !Pbar) return GDFT_BAD_ARGUMENT;
+  if (!aligned16(ws)) return GDFT_BAD_ALIGNMENT;
+  if (ws_bytes < eri_workspace(n)) return GDFT_WORKSPACE_TOO_SMALL;
+  return eri_jt_rows_launch(stream, n, rows, eri_rows, Jbar_rows, Pbar, ws);
 }
 
 extern "C" int gdft_xc_integrate_fwd(gdft_stream_t stream_, int64_t N, int F, int64_t c_rows, const double* c, const double* d,

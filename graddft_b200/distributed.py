@@ -9,7 +9,8 @@ collective exists on the path.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -28,14 +29,80 @@ def shard_bounds(N: int, rank: int, world: int, align: int = 128) -> Tuple[int, 
 _ROW_FIELDS = ("ao", "grad_ao", "grad_n_ao2", "chi", "weights", "coords")
 
 
-def shard_molecule_tensors(mol: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
-    """The rank's row block of every grid-sized tensor; everything else is passed through (replicated)."""
+def shard_molecule_tensors(mol: Dict[str, torch.Tensor], rank: int, world: int, shard_eri: bool = False) -> Dict[str, torch.Tensor]:
+    """The rank's row block of every grid-sized tensor; everything else is passed through (replicated).  With
+    `shard_eri` the (p,q) rows of rep_tensor are split as well: `rep_tensor` becomes the block [rows, n, n] and
+    `eri_row0` its first row (at n = 400 the tensor is 205 GB and cannot be replicated)."""
     N = int(mol["weights"].shape[0])
     lo, hi = shard_bounds(N, rank, world)
     out = dict(mol)
     for k in _ROW_FIELDS:
         if out.get(k) is not None:
             out[k] = out[k][lo:hi].contiguous()
+    if shard_eri and out.get("rep_tensor") is not None:
+        eri = out["rep_tensor"]
+        n = int(eri.shape[-1])
+        r0, r1 = shard_bounds(n * n, rank, world, align=32)  # 32 rows = one CTA pass of the sweep kernel
+        out["rep_tensor"] = eri.reshape(n * n, n, n)[r0:r1].contiguous()
+        out["eri_row0"] = r0
+    return out
+
+
+@dataclass(frozen=True)
+class GridShard:
+    """How a `Molecule` is spread over the process group: this rank holds grid rows [lo, hi) of every grid-sized
+    tensor and, when `eri_row0` is not None, the (p,q) rows [eri_row0, eri_row0 + rep_tensor.shape[0]) of
+    rep_tensor.  `energy_predictor` reads it from the molecule and closes each Fock build with one all-reduce."""
+
+    group: Any
+    rank: int
+    world: int
+    eri_row0: Optional[int] = None
+
+
+def attach_shard(molecule, shard: "GridShard"):
+    """Mark `molecule` (already holding this rank's rows) as one shard of a grid-sharded molecule.  The mark
+    survives `Molecule.replace`."""
+    object.__setattr__(molecule, "_shard", shard)
+    return molecule
+
+
+def shard_molecule(mol: Dict[str, torch.Tensor], rank: int, world: int, device=None, group=None, shard_eri: bool = False):
+    """`Molecule` holding rank `rank`'s shard of the tensor dict `mol` (keys as `molecule_from_tensors` takes them),
+    marked so that `energy_predictor` / the SCF loops all-reduce each Fock build over `group`."""
+    from .molecule import molecule_from_tensors
+
+    part = shard_molecule_tensors(mol, rank, world, shard_eri=shard_eri)
+    return attach_shard(molecule_from_tensors(part, device), GridShard(group, rank, world, part.get("eri_row0")))
+
+
+def local_coulomb(P: torch.Tensor, rep_tensor: torch.Tensor, shard: "GridShard") -> torch.Tensor:
+    """J as this rank can compute it: the full matrix when rep_tensor is replicated, else its own (p,q) rows written
+    into a zero matrix (the all-reduce that follows assembles the rest)."""
+    from . import ops
+
+    if shard.eri_row0 is None:
+        return ops.coulomb_j(P, rep_tensor)
+    n = int(P.shape[0])
+    J = torch.zeros(n * n, dtype=P.dtype, device=P.device)
+    rows = int(rep_tensor.shape[0])
+    J[shard.eri_row0:shard.eri_row0 + rows] = ops.coulomb_j_rows(P, rep_tensor)
+    return J.reshape(n, n)
+
+
+def allreduce_sum_packed(tensors: Sequence[torch.Tensor], group=None, skip: Sequence[int] = ()):
+    """Sum each tensor over the ranks of `group` with ONE collective on a flat float64 buffer; entries whose index is
+    in `skip` are already complete on every rank and are passed through untouched."""
+    idx = [i for i in range(len(tensors)) if i not in skip]
+    if not idx or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return list(tensors)
+    flat = torch.cat([tensors[i].reshape(-1) for i in idx])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    out, off = list(tensors), 0
+    for i in idx:
+        k = tensors[i].numel()
+        out[i] = flat[off:off + k].reshape(tensors[i].shape)
+        off += k
     return out
 
 

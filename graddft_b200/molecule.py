@@ -257,6 +257,8 @@ class Molecule:
             for k in ("_packed", "_omega_list"):
                 if k in self.__dict__:
                     object.__setattr__(new, k, self.__dict__[k])
+        if "_shard" in self.__dict__:
+            object.__setattr__(new, "_shard", self.__dict__["_shard"])
         return new
 
     @property

@@ -285,6 +285,55 @@ def coulomb_j(P: torch.Tensor, eri: torch.Tensor) -> torch.Tensor:
     return _CoulombJ.apply(P, eri)
 
 
+def _eri_rows_shape(P, eri_rows):
+    n = int(P.shape[0])
+    if tuple(P.shape) != (n, n) or eri_rows.dim() != 3 or tuple(eri_rows.shape[1:]) != (n, n) or eri_rows.shape[0] > n * n:
+        raise TypeError(f"rdm1 must be [n,n] and the rep_tensor row block [rows<=n*n, n, n]; got {tuple(P.shape)}, {tuple(eri_rows.shape)}")
+    return n, int(eri_rows.shape[0])
+
+
+class _CoulombJRows(Function):
+    """J entries of a contiguous block of (p,q) rows of rep_tensor (row-sharded ERI)."""
+
+    @staticmethod
+    def forward(ctx, P, eri_rows):
+        P, eri_rows = _c(P), _c(eri_rows)
+        n, rows = _eri_rows_shape(P, eri_rows)
+        ctx.save_for_backward(eri_rows)
+        out = torch.empty((rows,), dtype=F64, device=P.device)
+        with _timed("gdft_eri_jk"):
+            check(lib().gdft_eri_j_rows(stream_ptr(), n, rows, ptr(eri_rows), ptr(P), ptr(out)), "gdft_eri_j_rows")
+        return out
+
+    @staticmethod
+    def backward(ctx, Jbar_rows):
+        (eri_rows,) = ctx.saved_tensors
+        return _CoulombJRowsT.apply(Jbar_rows, eri_rows), None
+
+
+class _CoulombJRowsT(Function):
+    @staticmethod
+    def forward(ctx, Jbar_rows, eri_rows):
+        Jbar_rows = _c(Jbar_rows)
+        n, rows = int(eri_rows.shape[1]), int(eri_rows.shape[0])
+        ctx.save_for_backward(eri_rows)
+        out = torch.empty((n, n), dtype=F64, device=eri_rows.device)
+        ws = workspace(lib().gdft_workspace_bytes(_lib.OP_ERI_J, 0, n, 0, 0), eri_rows.device)
+        check(lib().gdft_eri_j_transpose_rows(stream_ptr(), n, rows, ptr(eri_rows), ptr(Jbar_rows), ptr(out), wptr(ws), ws.numel()),
+              "gdft_eri_j_transpose_rows")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (eri_rows,) = ctx.saved_tensors
+        return _CoulombJRows.apply(g, eri_rows), None
+
+
+def coulomb_j_rows(P: torch.Tensor, eri_rows: torch.Tensor) -> torch.Tensor:
+    """J[row0:row0+rows] (flattened (p,q) order) from the rank-local row block eri_rows[rows, n, n]."""
+    return _CoulombJRows.apply(P, eri_rows)
+
+
 def coulomb_k(P: torch.Tensor, eri: torch.Tensor) -> torch.Tensor:
     """K[p,r] = sum_qt (pq|rt) P[q,t]: same sweep, other index pairing (not in the reference; no VJP bound)."""
     L = lib()

@@ -54,26 +54,10 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
     if nlc_functional is not None:
         raise NotImplementedError("nlc_functional: the reference path raises NameError here (train.py:117-120)")
 
-    def predict(params, atoms: Molecule, *args) -> Tuple[Array, Array]:
-        exc, fock_xc, at = xc_energy_and_grads(functional, params, atoms.rdm1, atoms, *args)
-        differentiable = fock_xc.requires_grad
-        P = atoms.rdm1.sum(dim=0)
-        if differentiable or atoms.rdm1.requires_grad:
-            J = ops.coulomb_j(P, atoms.rep_tensor)
-            EJ = (P * J).sum() / 2.0
-        else:
-            J, EJ = ops.coulomb_j_and_energy(P, atoms.rep_tensor)
-        energy = exc + (atoms.nuclear_repulsion + (P * atoms.h1e).sum() + EJ)  # train.py:150, molecule.py:727-733
-
-        if fock_xc.requires_grad or J.requires_grad:
-            fock = atoms.h1e + J + fock_xc
-            fock = abs_clip(fock, clip_cte)
-            fock = 0.5 * (fock + fock.transpose(1, 2))
-            fock = abs_clip(fock, clip_cte)
-        else:
-            fock = ops.fock_assemble(atoms.h1e, J, fock_xc, clip_cte)  # train.py:148-163 in one kernel
-
-        # train.py:165-198: features for the explicit terms (cached on `at`, so nothing is recomputed)
+    def explicit_terms(params, at: Molecule, differentiable: bool, *args):
+        """train.py:165-213: the explicit exact-exchange Fock terms V (one per HF route of the functional); the
+        features they need are cached on `at`, so nothing is recomputed.  They do not depend on the Fock matrix
+        being assembled, only on (params, rdm1)."""
         with torch.set_grad_enabled(differentiable):
             if functional.energy_densities and functional.densitygrads:
                 grad_densities = functional.energy_densities(at, *args, **kwargs)
@@ -104,11 +88,48 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
         def detached(t):
             return t.detach() if isinstance(t, torch.Tensor) else t
 
+        terms = []
         if functional.densitygrads:
-            vxc_expl = functional.densitygrads(functional, params, at, nograd_densities, detached(cinputs), detached(grad_densities))
-            fock = _add_sym(fock, vxc_expl, clip_cte)
+            terms.append(functional.densitygrads(functional, params, at, nograd_densities, detached(cinputs), detached(grad_densities)))
         if functional.coefficient_input_grads:
-            vxc_expl = functional.coefficient_input_grads(functional, params, at, nograd_cinputs, detached(grad_cinputs), detached(densities))
+            terms.append(functional.coefficient_input_grads(functional, params, at, nograd_cinputs, detached(grad_cinputs), detached(densities)))
+        return terms
+
+    def predict(params, atoms: Molecule, *args) -> Tuple[Array, Array]:
+        shard = atoms.__dict__.get("_shard")
+        exc, fock_xc, at = xc_energy_and_grads(functional, params, atoms.rdm1, atoms, *args)
+        differentiable = fock_xc.requires_grad
+        P = atoms.rdm1.sum(dim=0)
+        if shard is not None:
+            # grid rows (and optionally the (p,q) rows of rep_tensor) live on `world` GPUs: every grid-derived
+            # quantity below is a partial sum; ONE all-reduce of [E_xc | V_xc | J | V_HF...] closes the build
+            if differentiable or atoms.rdm1.requires_grad:
+                raise NotImplementedError("the grid-sharded predictor is first-order in params only (no create_graph through the Fock matrix)")
+            from . import distributed as gdist
+            vterms = explicit_terms(params, at, False, *args)
+            J = gdist.local_coulomb(P, atoms.rep_tensor, shard)
+            (exc_sum, fock_xc, J, *vterms) = gdist.allreduce_sum_packed(
+                [exc.detach(), fock_xc, J, *vterms], group=shard.group, skip=() if shard.eri_row0 is not None else (2,))
+            exc = exc + (exc_sum - exc.detach()) if exc.requires_grad else exc_sum  # value: the global sum; gradient: identity
+            EJ = (P * J).sum() / 2.0
+        elif differentiable or atoms.rdm1.requires_grad:
+            J = ops.coulomb_j(P, atoms.rep_tensor)
+            EJ = (P * J).sum() / 2.0
+        else:
+            J, EJ = ops.coulomb_j_and_energy(P, atoms.rep_tensor)
+        energy = exc + (atoms.nuclear_repulsion + (P * atoms.h1e).sum() + EJ)  # train.py:150, molecule.py:727-733
+
+        if fock_xc.requires_grad or J.requires_grad:
+            fock = atoms.h1e + J + fock_xc
+            fock = abs_clip(fock, clip_cte)
+            fock = 0.5 * (fock + fock.transpose(1, 2))
+            fock = abs_clip(fock, clip_cte)
+        else:
+            fock = ops.fock_assemble(atoms.h1e, J, fock_xc, clip_cte)  # train.py:148-163 in one kernel
+
+        if shard is None:
+            vterms = explicit_terms(params, at, differentiable, *args)
+        for vxc_expl in vterms:  # train.py:200-213: fock += V + V^T, clip after each
             fock = _add_sym(fock, vxc_expl, clip_cte)
         fock = abs_clip(fock, clip_cte)
         return energy, fock

@@ -135,6 +135,15 @@ int gdft_eri_jk(gdft_stream_t stream, int64_t n, const double* eri /*[n,n,n,n]*/
 int gdft_eri_j_transpose(gdft_stream_t stream, int64_t n, const double* eri, const double* Jbar,
                          double* Pbar, void* ws, size_t ws_bytes);
 
+/* Row-sharded sweep (at n = 400 the tensor is 205 GB and must be split over GPUs):
+ * `eri_rows` is the contiguous block of `rows` (p,q)-rows [rows, n*n] a rank holds; J_rows[rows] are the matching
+ * entries of J (row-major (p,q) order).  Per-row summation order is independent of the blocking, so the gathered J
+ * is bitwise equal to gdft_eri_jk's.  The transpose returns this block's partial Pbar (sum over ranks = full). */
+int gdft_eri_j_rows(gdft_stream_t stream, int64_t n, int64_t rows, const double* eri_rows, const double* P,
+                    double* J_rows);
+int gdft_eri_j_transpose_rows(gdft_stream_t stream, int64_t n, int64_t rows, const double* eri_rows,
+                              const double* Jbar_rows, double* Pbar, void* ws, size_t ws_bytes);
+
 /* ---- K6: XC quadrature ------------------------------------------------------------------------
  * E = sum_r aclip(w_r) aclip(aclip(sum_f c[r,f] d[r,f]))  (grad_dft/functional.py:251-253,342;
  * aclip = abs_clip, grad_dft/molecule.py:687-689).  c_rows is 1 (constant functionals,

@@ -105,3 +105,46 @@ def test_allreduce_gradients_world2_gloo():
         tot = res[0][1][k] + res[1][1][k]
         assert torch.allclose(res[0][3][k], tot, rtol=0, atol=1e-15) and torch.allclose(res[1][3][k], tot, rtol=0, atol=1e-15)
     assert abs(res[0][4] - (res[0][2] + res[1][2])) < 1e-15
+
+
+def test_shard_eri_rows_cover():
+    n = 7
+    mol = {"weights": torch.rand(300, dtype=torch.float64), "ao": torch.randn(300, n, dtype=torch.float64),
+           "rep_tensor": torch.randn(n, n, n, n, dtype=torch.float64)}
+    parts = [gdist.shard_molecule_tensors(mol, r, 3, shard_eri=True) for r in range(3)]
+    assert torch.equal(torch.cat([p["rep_tensor"] for p in parts]).reshape(n, n, n, n), mol["rep_tensor"])
+    assert parts[0]["eri_row0"] == 0
+    for a, b in zip(parts, parts[1:]):
+        assert b["eri_row0"] == a["eri_row0"] + a["rep_tensor"].shape[0]
+
+
+def _packed_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(11 + rank)
+    ts = [torch.randn((), generator=g, dtype=torch.float64), torch.randn(2, 3, 3, generator=g, dtype=torch.float64),
+          torch.full((3, 3), 5.0, dtype=torch.float64), torch.randn(2, 3, 3, generator=g, dtype=torch.float64)]
+    out = gdist.allreduce_sum_packed(ts, skip=(2,))
+    q.put((rank, [t.clone() for t in ts], [t.clone() for t in out]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_sum_packed_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_packed_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for k in (0, 1, 3):
+        tot = res[0][1][k] + res[1][1][k]
+        for r in res:
+            assert torch.allclose(r[2][k], tot, rtol=0, atol=1e-15)
+    for r in res:  # the skipped entry is passed through untouched
+        assert torch.equal(r[2][2], torch.full((3, 3), 5.0, dtype=torch.float64))

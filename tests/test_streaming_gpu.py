@@ -118,6 +118,36 @@ def test_eri_sweep(cuda_device, n):
     assert relerr(ops.coulomb_j(P_d, eri_ns.to(dev)), oracle.coulomb_potential(P, eri_ns)) < RTOL
 
 
+@pytest.mark.parametrize("n,world", [(12, 2), (43, 3), (64, 8)])
+def test_eri_row_sharded_sweep(cuda_device, n, world):
+    """Row-sharded J: gathered row blocks are bitwise the unsharded sweep, and the blocks'
+    transposed sweeps sum to the unsharded VJP."""
+    from graddft_b200 import distributed as gdist
+
+    g = torch.Generator().manual_seed(5)
+    eri = torch.randn(n, n, n, n, generator=g, dtype=F64)
+    P = torch.randn(n, n, generator=g, dtype=F64)
+    Jbar = torch.randn(n, n, generator=g, dtype=F64)
+    dev = cuda_device
+    J_full = ops.coulomb_j(P.to(dev), eri.to(dev))
+    Pl = P.to(dev).clone().requires_grad_(True)
+    (vjp_full,) = torch.autograd.grad((ops.coulomb_j(Pl, eri.to(dev)) * Jbar.to(dev)).sum(), Pl)
+    rows, vjp = [], torch.zeros(n, n, dtype=F64, device=dev)
+    for r in range(world):
+        part = gdist.shard_molecule_tensors({"weights": torch.zeros(8, dtype=F64), "rep_tensor": eri}, r, world, shard_eri=True)
+        blk = part["rep_tensor"].to(dev)
+        Pl = P.to(dev).clone().requires_grad_(True)
+        Jr = ops.coulomb_j_rows(Pl, blk)
+        rows.append(Jr.detach())
+        r0 = part["eri_row0"]
+        if blk.shape[0]:
+            (v,) = torch.autograd.grad((Jr * Jbar.to(dev).reshape(-1)[r0:r0 + blk.shape[0]]).sum(), Pl)
+            vjp += v
+    assert torch.equal(torch.cat(rows).reshape(n, n), J_full)
+    assert relerr(vjp, vjp_full.cpu()) < RTOL
+    assert relerr(J_full, oracle.coulomb_potential(P, eri)) < RTOL
+
+
 @pytest.mark.parametrize("N,F,crows", [(1, 1, 1), (1000, 5, 1), (4097, 3, 4097), (300001, 5, 1), (70000, 20, 70000)])
 def test_xc_integrate(cuda_device, N, F, crows):
     g = torch.Generator().manual_seed(N + F)
