@@ -148,6 +148,130 @@ def measure_dgemm_tflops(dev, m=8192, reps=5):
     return 2.0 * m ** 3 / best / 1e9
 
 
+
+# ---------------------------------------------------------------------------------------------------------
+# second headline metric: jitted-SCF iterations/s (diff_scf_loop = make_jitted_scf_loop, grad_dft/evaluate.py:917)
+# ---------------------------------------------------------------------------------------------------------
+SCF_SHAPES = {
+    # BASELINE.json configs[1]: H2O / def2-TZVP (n = 43), level-3 grid (~34k points), B3LYP
+    "c2": dict(N=34_000, n=43, desc="H2O/def2-TZVP-shaped: 34k grid pts x 43 AOs, B3LYP (LSDA+B88+VWN+LYP+HF), DIIS SCF"),
+    # benzene / def2-TZVP-shaped (configs[2] shape), B3LYP; rep_tensor 38.9 GB
+    "c3": dict(N=500_000, n=264, desc="benzene/def2-TZVP-shaped: 500k grid pts x 264 AOs, B3LYP, DIIS SCF, rep_tensor 38.9 GB"),
+}
+
+
+def _scf_shard(N, n, rank, world, dev):
+    """Rank-local shard of a synthetic B3LYP-ready molecule: grid rows seeded per rank, n x n data replicated, the
+    (p,q) rows of an 8-fold-symmetric PSD rep_tensor built directly as a row block (never materialised whole)."""
+    from graddft_b200 import distributed as gdist
+    from graddft_b200.synthetic import synthetic_molecule
+
+    lo, hi = gdist.shard_bounds(N, rank, world)
+    mol = synthetic_molecule(hi - lo, n, n_omega=1, seed=1984 + rank, device=dev, with_eri=False, mask_frac=0.0)
+    small = synthetic_molecule(8, n, seed=1984, device=dev, with_eri=False)
+    for k in ("rdm1", "mo_coeff", "mo_occ", "mo_energy", "h1e", "s1e", "nuclear_repulsion"):
+        mol[k] = small[k]
+    mol["weights"] = mol["weights"] * ((hi - lo) / N)
+    mol["omegas"] = [0.0]
+    g = torch.Generator(device=dev).manual_seed(4242)
+    Q = 2 * n
+    B = torch.randn(Q, n, n, generator=g, dtype=torch.float64, device=dev)
+    B2 = (0.5 * (B + B.transpose(1, 2))).reshape(Q, n * n)
+    r0, r1 = gdist.shard_bounds(n * n, rank, world, align=32) if world > 1 else (0, n * n)
+    mol["rep_tensor"] = (B2[:, r0:r1].T @ B2).div_(Q).reshape(r1 - r0, n, n)
+    del B, B2
+    if world == 1:
+        mol["rep_tensor"] = mol["rep_tensor"].reshape(n, n, n, n)
+        return gdist_molecule(mol, dev, None)
+    return gdist_molecule(mol, dev, gdist.GridShard(None, rank, world, r0))
+
+
+def gdist_molecule(mol, dev, shard):
+    import graddft_b200 as gd
+    from graddft_b200 import distributed as gdist
+
+    m = gd.molecule_from_tensors(mol, dev)
+    if shard is not None:
+        gdist.attach_shard(m, shard)
+    m.packed_basis
+    return m
+
+
+def scf_leg(shape_key, rank, world, dev, timed_ms, dgemm_tf, hbm_gbs):
+    """ms per SCF iteration of diff_scf_loop(B3LYP): slope between a 2-cycle and a 6-cycle run (each iteration =
+    DIIS extrapolation + generalised eigenproblem + occupations + rdm1 + one full Fock build)."""
+    import graddft_b200 as gd
+    from graddft_b200 import ops
+
+    sh = SCF_SHAPES[shape_key]
+    N, n = sh["N"], sh["n"]
+    m = _scf_shard(N, n, rank, world, dev)
+    loops = {c: gd.diff_scf_loop(gd.B3LYP, cycles=c) for c in (2, 6)}
+    out = None
+    for c in (2, 6):
+        out = loops[c](None, m)  # warm-up (workspaces, cuSOLVER handles)
+    ms = {}
+    for c in (2, 6):
+        ms[c] = min(timed_ms(lambda: loops[c](None, m), 1) for _ in range(3))
+    per_iter = (ms[6] - ms[2]) / 4.0
+    ops.TIMING = {}
+    out = loops[2](None, m)
+    torch.cuda.synchronize()
+    timing, ops.TIMING = ops.TIMING, None
+
+    def avg(name):
+        ev = timing.get(name, [])
+        return sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
+
+    res = {"workload": sh["desc"], "N": N, "n": n, "iter_per_s": 1e3 / per_iter, "ms_per_iter": per_iter,
+           "ms_loop_2_cycles": ms[2], "ms_loop_6_cycles": ms[6], "energy_finite": bool(torch.isfinite(out.energy))}
+    if rank == 0:
+        rows = m.rep_tensor.shape[0] * (m.rep_tensor.shape[1] if m.rep_tensor.dim() == 4 else 1)
+        eri_ms = avg("gdft_eri_jk")
+        eri_bytes = 8.0 * rows * n * n
+        res["kernels_ms"] = {"density_fwd": avg("gdft_density_fwd"), "density_bwd": avg("gdft_density_bwd"), "eri_j": eri_ms}
+        if eri_bytes > 2.5e8:  # larger than L2: a DRAM figure
+            res["roofline_eri"] = {"bound": "hbm", "kernel": "eri_j_kernel (rep_tensor (pq)x(rt) sweep)", "achieved": eri_bytes / eri_ms / 1e6,
+                                   "peak": hbm_gbs[0], "unit": "GB/s", "frac": eri_bytes / eri_ms / 1e6 / hbm_gbs[0],
+                                   "bytes_per_launch": eri_bytes, "ms_per_launch": eri_ms, "peak_source": hbm_gbs[1]}
+        # roofline of one iteration: B3LYP Fock build = 16 GEMM units (rho, grad, lapl fwd + VJP) + 2 (HF Fock) at the
+        # measured DGEMM rate, plus one rep_tensor sweep at the HBM peak (per-GPU shares)
+        unit = 2.0 * (N / world) * n * n
+        t_roof = 18.0 * unit / (dgemm_tf * 1e9) + eri_bytes / (hbm_gbs[0] * 1e6)
+        res["roofline_iter"] = {"ms_at_roofline": t_roof, "frac": t_roof / per_iter,
+                                "model": "18 units x 2*N*n^2 FLOP at measured cuBLAS DGEMM + 8*rows*n^2 B at HBM peak"}
+    del m, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_scf_iter_rate(N, n):
+    """Oracle SCF iteration (B3LYP) on the host cores: slope between 1- and 3-cycle loops."""
+    import oracle
+    from graddft_b200.synthetic import synthetic_molecule
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    mol = synthetic_molecule(N, n, n_omega=1, seed=1984, mask_frac=0.0)
+    t = {}
+    for c in (1, 3):
+        t0 = time.perf_counter()
+        oracle.diff_scf_loop_energy(mol, oracle.predict_b3lyp, c)
+        t[c] = time.perf_counter() - t0
+    per_iter = (t[3] - t[1]) / 2.0
+    return 1.0 / per_iter, cores, per_iter
+
+
+def hbm_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs ('of measured')"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s ('of fallback': MEASURED_PEAKS.json absent)"
+
+
 def run_ours(args, wl):
     import torch.distributed as dist
 
@@ -245,6 +369,24 @@ def run_ours(args, wl):
     clocks = sampler.stop() if rank == 0 else None
     torch.cuda.synchronize()
 
+    packed_gb = 4 * Nloc * molecule.packed_basis.npad * 8 / 1e9
+    scf = None
+    if not args.no_scf:
+        del molecule
+        torch.cuda.empty_cache()
+        if world > 1:
+            dgemm_all = torch.tensor([dgemm_tf or 0.0], dtype=torch.float64, device=dev)
+            dist.broadcast(dgemm_all, 0)
+            dgemm_tf_all = float(dgemm_all)
+        else:
+            dgemm_tf_all = dgemm_tf
+        scf = {}
+        for key in (("c2", "c3") if world == 1 else ("c3",)):
+            try:
+                scf[key] = scf_leg(key, rank, world, dev, timed, dgemm_tf_all, hbm_peak())
+            except Exception as exc:  # the headline XC line must survive a failure of the secondary leg
+                scf[key] = {"error": f"{type(exc).__name__}: {exc}"}
+
     # sanity: the result that went to the host is finite
     assert bool(torch.isfinite(out_host).all()), "non-finite XC build"
 
@@ -276,7 +418,7 @@ def run_ours(args, wl):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["desc"], "N": N, "n": n, "rows_per_gpu": Nloc, "functional": "B88 (LSDA+B88 columns)",
                        "parallelism": f"grid-sharded x{world}, one all-reduce of [E_xc|V_xc] per build" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (packed basis %.1f GB per GPU)" % (4 * Nloc * molecule.packed_basis.npad * 8 / 1e9)},
+                       "l2": "inputs larger than L2 (packed basis %.1f GB per GPU)" % packed_gb},
             "e2e": {"value": e2e, "unit": "builds/s", "h2d_bytes_per_step": rdm1_host.numel() * 8, "d2h_bytes_per_step": out_host.numel() * 8,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
@@ -292,6 +434,12 @@ def run_ours(args, wl):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if scf is not None:
+            if world == 1 and not args.no_cpu_baseline and "error" not in scf.get("c2", {"error": 1}):
+                rate, cores_s, dt = cpu_scf_iter_rate(SCF_SHAPES["c2"]["N"], SCF_SHAPES["c2"]["n"])
+                scf["c2"]["cpu_baseline"] = {"value": rate, "unit": "iter/s", "cores": cores_s, "kind": "port",
+                                             "sample": f"full H2O-shaped molecule, oracle diff_scf_loop (torch-CPU float64), {dt * 1e3:.0f} ms/iter"}
+            line["scf"] = {"metric": "jitted_scf_iter_per_s (diff_scf_loop = make_jitted_scf_loop)", "unit": "iter/s", **scf}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -305,6 +453,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-scf", dest="no_scf", action="store_true", help="skip the secondary SCF-iteration leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
