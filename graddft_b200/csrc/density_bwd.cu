@@ -35,11 +35,16 @@ constexpr int BWD_MAX_MT = 5;
 struct BwdTerm {
   int a_plane, nq, slot_plane0, per_spin, coef_row0;
 };
+// Tiles come in (at most) two sizes per dimension -- `rem` big tiles of base+1 sub-tiles first, then tc-rem small
+// ones of `base` -- hence four tile classes c = 2*(a small) + (b small).  Each class has its own K-split count
+// ks_class[c], proportional to the class's DMMA work per k-step, so that every CTA carries the same amount of work
+// (a single K-split for all tiles makes the CTAs of the big tiles the stragglers of every wave).
 struct BwdParams {
-  int64_t N, rows_per_split;
-  int npad, nsub, nterms, tiles_b, stages, maxq;
+  int64_t N;
+  int npad, nsub, nterms, tc, base, rem, stages, maxq;
+  int ks_class[4], cta_prefix[5];
   BwdTerm terms[4];
-  double* part;  // [ksplit][2][npad][npad]
+  double* part;  // [kmax][2][npad][npad]
 };
 
 // Fragments of one 4-row k-step of one warp: a[i] = A[k][i*8+g], b[j] = sum_q coef_q[k] * plane_q[k][j*8+g]
@@ -76,7 +81,7 @@ struct BwdWarpCtx {
   int stage_elems, S, ktiles, maxq, spin, lane;
   int a_off, b_off;  // element offsets of this warp's fragment origin inside the A / plane tiles (t*PITCH + off + g)
   int a_row, b_col;  // global row / column of the warp tile's (0,0) element (+g / +2t added at the store)
-  int g, t;
+  int g, t, split;
 };
 
 // One term (ktiles k-tiles starting at ring position st/ph) of one consumer warp, software-pipelined over the
@@ -137,7 +142,7 @@ __device__ __forceinline__ void bwd_consumer(const BwdParams& p, const BwdWarpCt
     }
   }
 
-  double* out = p.part + ((size_t)blockIdx.y * 2 + w.spin) * p.npad * p.npad;
+  double* out = p.part + ((size_t)w.split * 2 + w.spin) * p.npad * p.npad;
 #pragma unroll
   for (int i = 0; i < MI; i++) {
     const int a = w.a_row + i * 8 + w.g;
@@ -163,15 +168,23 @@ density_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* empty = full + BWD_MAX_STAGES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  // balanced tiling: the npad/8 sub-tiles of each dimension are split over p.tiles_b tiles as evenly as possible
-  // (sizes differ by at most one sub-tile), and each tile's sub-tiles evenly over its two warps
-  const int ta = blockIdx.x / p.tiles_b, tb = blockIdx.x - ta * p.tiles_b;
-  const int sub_base = p.nsub / p.tiles_b, sub_rem = p.nsub - sub_base * p.tiles_b;
-  const int a_sub0 = ta * sub_base + min(ta, sub_rem), na = sub_base + (ta < sub_rem ? 1 : 0);
-  const int b_sub0 = tb * sub_base + min(tb, sub_rem), nb = sub_base + (tb < sub_rem ? 1 : 0);
+  // CTA -> (tile class, K-split, tile): classes are laid out one after the other
+  int cls = 0;
+  while (cls < 3 && (int)blockIdx.x >= p.cta_prefix[cls + 1]) cls++;
+  const int local = (int)blockIdx.x - p.cta_prefix[cls];
+  const int ks = p.ks_class[cls];
+  const int a_small = cls >> 1, b_small = cls & 1;
+  const int nb_c = b_small ? p.tc - p.rem : p.rem, ntile_c = (a_small ? p.tc - p.rem : p.rem) * nb_c;
+  // tiles fastest: CTAs resident together stream the same grid rows (their A / plane tiles hit in L2)
+  const int split = local / ntile_c, tile = local - split * ntile_c;
+  const int ta = tile / nb_c + (a_small ? p.rem : 0), tb = tile - (tile / nb_c) * nb_c + (b_small ? p.rem : 0);
+  const int a_sub0 = ta * p.base + min(ta, p.rem), na = p.base + (a_small ? 0 : 1);
+  const int b_sub0 = tb * p.base + min(tb, p.rem), nb = p.base + (b_small ? 0 : 1);
   const int a0 = a_sub0 * 8, b0 = b_sub0 * 8;
-  const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
-  const int64_t r_end = min(p.N, r_begin + p.rows_per_split);
+  const int64_t ktiles_total = (p.N + BKR - 1) / BKR;
+  const int64_t kt_per = (ktiles_total + ks - 1) / ks;
+  const int64_t r_begin = (int64_t)split * kt_per * BKR;
+  const int64_t r_end = min(p.N, r_begin + kt_per * BKR);
   const int ktiles = r_end > r_begin ? (int)((r_end - r_begin + BKR - 1) / BKR) : 0;
   const int total = p.nterms * ktiles;
   const int S = p.stages;
@@ -215,7 +228,7 @@ density_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   w.sStage = sStage; w.full = full; w.empty = empty;
   w.stage_elems = stage_elems; w.S = S; w.ktiles = ktiles; w.maxq = p.maxq; w.spin = spin; w.lane = lane;
   w.a_off = t * PITCH + row_off + g; w.b_off = t * PITCH + col_off + g;
-  w.a_row = a0 + row_off; w.b_col = b0 + col_off; w.g = g; w.t = t;
+  w.a_row = a0 + row_off; w.b_col = b0 + col_off; w.g = g; w.t = t; w.split = split;
   if (mi == MT && nj == MT) bwd_consumer<MT, MT, MT>(p, w);
   else if (MT > 1 && mi == MT && nj == MT - 1) bwd_consumer<MT, MT, (MT > 1 ? MT - 1 : 1)>(p, w);
   else if (MT > 1 && mi == MT - 1 && nj == MT) bwd_consumer<MT, (MT > 1 ? MT - 1 : 1), MT>(p, w);
@@ -231,13 +244,15 @@ density_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-// out[s][a][b] = scale * sum_ks part[ks][s][a][b]   (fixed summation order)
-__global__ void bwd_reduce_kernel(const double* __restrict__ part, int ksplit, int npad, int n, double scale,
-                                  double* __restrict__ out) {
+// out[s][a][b] = scale * sum_{k < ks(tile class of (a,b))} part[k][s][a][b]   (fixed summation order)
+__global__ void bwd_reduce_kernel(const double* __restrict__ part, int4 ks_class, int big_end /*first column of the small tiles*/,
+                                  int npad, int n, double scale, double* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = 2 * n * n;
   if (idx >= total) return;
   const int s = idx / (n * n), rem = idx - s * n * n, a = rem / n, b = rem - a * n;
+  const int cls = (a >= big_end ? 2 : 0) + (b >= big_end ? 1 : 0);
+  const int ksplit = cls == 0 ? ks_class.x : cls == 1 ? ks_class.y : cls == 2 ? ks_class.z : ks_class.w;
   const size_t off = ((size_t)s * npad + a) * npad + b;
   const size_t stride = (size_t)2 * npad * npad;
   double acc = 0.0;
@@ -278,8 +293,8 @@ __global__ void hf_coef_kernel(int64_t N, int64_t Npad, const double* __restrict
 }
 
 struct BwdPlan {
-  int mt, tiles_a, tiles_b, ksplit, stages;
-  int64_t rows_per_split;
+  int mt, tc, base, rem, kmax, stages, ctas;
+  int ks_class[4], cta_prefix[5];
   size_t smem;
 };
 
@@ -307,30 +322,63 @@ static BwdPlan plan_bwd(int64_t N, int npad, int maxq) {
     if (v >= 1 && v <= nsub && (((nsub + v - 1) / v) + 1) / 2 <= BWD_MAX_MT) { best_tc = v; best_mt = (((nsub + v - 1) / v) + 1) / 2; }
   }
   pl.mt = best_mt;
+  pl.tc = best_tc;
+  pl.base = nsub / best_tc;
+  pl.rem = nsub - pl.base * best_tc;
   const int T = 16 * best_mt;
-  pl.tiles_a = pl.tiles_b = best_tc;
-  const int ntiles = pl.tiles_a * pl.tiles_b;
-  const int slots = 148;  // one resident CTA per SM
+
+  // Work-balanced split-K.  Class c = 2*(a small) + (b small); its per-k-step work is that of its busiest warp
+  // (+1: the fragment loads and ring bookkeeping every k-step pays).  The CTA budget is a whole number of waves of
+  // 148 (one resident CTA per SM), as many waves as leave >= 16 k-tiles per split (more, shorter waves: the tail is
+  // ~1/waves of the run), shared among the classes in proportion to count x work.
+  const int nbig = pl.rem, nsmall = best_tc - pl.rem;
+  const int count[4] = {nbig * nbig, nbig * nsmall, nsmall * nbig, nsmall * nsmall};
+  const int hb = (pl.base + 2) / 2, hs = (pl.base + 1) / 2;  // ceil(size/2) of a big / small tile
+  const double work[4] = {hb * hb + 1.0, hb * hs + 1.0, hs * hb + 1.0, hs * hs + 1.0};
+  double total_work = 0.0;
+  int ntiles = 0;
+  for (int c = 0; c < 4; c++) { total_work += count[c] * work[c]; ntiles += count[c]; }
   const int64_t ktiles_total = (N + BWD_BKR - 1) / BWD_BKR;
-  // K-splits: fill whole waves of 148 CTAs; prefer more, shorter waves (tail effect ~ 1/waves) while each
-  // split still streams >= 64 k-tiles
-  int best_ks = 1;
-  double best_eff = -1.0;
-  for (int ks = 1; ks <= 1024; ks++) {
-    if ((int64_t)ks * 64 > ktiles_total && ks > 1) break;
-    const int64_t ctas = (int64_t)ks * ntiles;
-    if (ctas > 4096) break;
-    const double waves = (double)((ctas + slots - 1) / slots);
-    const double eff = (double)ctas / (waves * slots) - 0.0005 * ks;
-    if (eff > best_eff) { best_eff = eff; best_ks = ks; }
+  int waves = 8;
+  if (const char* e = getenv("GDFT_BWD_WAVES")) { int v = atoi(e); if (v >= 1 && v <= 16) waves = v; }
+  while (waves > 1 && (int64_t)148 * waves * 16 > ktiles_total * ntiles) waves--;
+  int budget = 148 * waves;
+  if (budget < ntiles) budget = ntiles;
+  int ks[4], used = 0;
+  double frac[4];
+  for (int c = 0; c < 4; c++) {
+    ks[c] = 0;
+    frac[c] = -1.0;
+    if (!count[c]) continue;
+    const double ideal = budget * work[c] / total_work;  // K-splits per tile of this class
+    ks[c] = (int)ideal;
+    if (ks[c] < 1) ks[c] = 1;
+    if ((int64_t)ks[c] > ktiles_total) ks[c] = (int)(ktiles_total > 0 ? ktiles_total : 1);
+    frac[c] = ideal - ks[c];
+    used += ks[c] * count[c];
   }
-  pl.ksplit = best_ks;
-  pl.rows_per_split = round_up((N + best_ks - 1) / best_ks, BWD_BKR);
+  for (;;) {  // hand the CTAs left over by the rounding to the classes with the largest fractional parts
+    int bestc = -1;
+    for (int c = 0; c < 4; c++)
+      if (count[c] && frac[c] > 0.0 && used + count[c] <= budget && (int64_t)ks[c] < ktiles_total && (bestc < 0 || frac[c] > frac[bestc])) bestc = c;
+    if (bestc < 0) break;
+    ks[bestc]++;
+    frac[bestc] -= 1.0;
+    used += count[bestc];
+  }
+  pl.kmax = 1;
+  pl.cta_prefix[0] = 0;
+  for (int c = 0; c < 4; c++) {
+    pl.ks_class[c] = ks[c];
+    pl.cta_prefix[c + 1] = pl.cta_prefix[c] + ks[c] * count[c];
+    if (ks[c] > pl.kmax) pl.kmax = ks[c];
+  }
+  pl.ctas = pl.cta_prefix[4];
   const size_t stage_bytes = (size_t)(BWD_BKR * (T + 4) * (1 + maxq) + BWD_BKR * BWD_COEF_W) * 8;
   const size_t fixed = 2 * BWD_MAX_STAGES * 8 + 128;
-  const size_t budget = 227 * 1024;
+  const size_t smem_budget = 227 * 1024;
   pl.stages = BWD_MAX_STAGES;
-  while (pl.stages > 2 && pl.stages * stage_bytes + fixed > budget) pl.stages--;
+  while (pl.stages > 2 && pl.stages * stage_bytes + fixed > smem_budget) pl.stages--;
   pl.smem = pl.stages * stage_bytes + fixed;
   return pl;
 }
@@ -340,7 +388,7 @@ size_t density_bwd_workspace(int64_t N, int64_t n, int, int) {
   const int npad = (int)npad_of(n);
   BwdPlan pl = plan_bwd(N, npad, BWD_MAX_SLOTS);
   size_t w_bytes = ((size_t)round_up(N, BWD_BKR) * BWD_COEF_W * 8 + 255) & ~size_t(255);
-  size_t part_bytes = ((size_t)pl.ksplit * 2 * npad * npad * 8 + 255) & ~size_t(255);
+  size_t part_bytes = ((size_t)pl.kmax * 2 * npad * npad * 8 + 255) & ~size_t(255);
   return w_bytes + part_bytes + 512;
 }
 
@@ -348,8 +396,7 @@ template <int MT>
 static int launch_bwd_t(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmP, const CUtensorMap& tmW,
                         const BwdPlan& pl, const BwdParams& p) {
   GDFT_CUDA_TRY(cudaFuncSetAttribute(density_bwd_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  dim3 grid(pl.tiles_a * pl.tiles_b, pl.ksplit);
-  density_bwd_kernel<MT><<<grid, BWD_THREADS, pl.smem, stream>>>(tmA, tmP, tmW, p);
+  density_bwd_kernel<MT><<<(unsigned)pl.ctas, BWD_THREADS, pl.smem, stream>>>(tmA, tmP, tmW, p);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
@@ -372,8 +419,10 @@ static int run_bwd(cudaStream_t stream, int64_t N, int n, int nplanes_a, const d
   if ((rc = make_tmap_3d(&tmW, W, (uint64_t)Npad, BWD_COEF_W, 1, (uint64_t)Npad * 8, (uint64_t)Npad * BWD_COEF_W * 8, BWD_BKR, BWD_COEF_W)))
     return rc;
   BwdParams p{};
-  p.N = N; p.rows_per_split = pl.rows_per_split; p.npad = npad; p.nsub = npad / 8; p.nterms = nterms; p.tiles_b = pl.tiles_b; p.stages = pl.stages;
+  p.N = N; p.npad = npad; p.nsub = npad / 8; p.nterms = nterms; p.tc = pl.tc; p.base = pl.base; p.rem = pl.rem; p.stages = pl.stages;
   p.maxq = maxq;
+  for (int c = 0; c < 4; c++) p.ks_class[c] = pl.ks_class[c];
+  for (int c = 0; c < 5; c++) p.cta_prefix[c] = pl.cta_prefix[c];
   for (int i = 0; i < nterms; i++) p.terms[i] = terms[i];
   p.part = part;
   switch (pl.mt) {
@@ -385,7 +434,8 @@ static int run_bwd(cudaStream_t stream, int64_t N, int n, int nplanes_a, const d
   }
   if (rc) return rc;
   const int total = 2 * n * n;
-  bwd_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(part, pl.ksplit, npad, n, scale, out);
+  bwd_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(part, make_int4(pl.ks_class[0], pl.ks_class[1], pl.ks_class[2], pl.ks_class[3]),
+                                                             pl.rem * (pl.base + 1) * 8, npad, n, scale, out);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
@@ -415,7 +465,7 @@ extern "C" int gdft_density_bwd(gdft_stream_t stream_, int64_t N, int64_t n, int
   BwdPlan pl = plan_bwd(N, npad, BWD_MAX_SLOTS);  // ksplit does not depend on the slot count
   Workspace wsp(ws, ws_bytes);
   double* W = wsp.take<double>((size_t)round_up(N, BWD_BKR) * BWD_COEF_W);
-  double* part = wsp.take<double>((size_t)pl.ksplit * 2 * npad * npad);
+  double* part = wsp.take<double>((size_t)pl.kmax * 2 * npad * npad);
   if (!W || !part) return GDFT_WORKSPACE_TOO_SMALL;
 
   const int64_t Npad = round_up(N, BWD_BKR);
@@ -449,7 +499,7 @@ extern "C" int gdft_hf_fock(gdft_stream_t stream_, int64_t N, int64_t n, int Wn,
   BwdPlan pl = plan_bwd(N, npad, BWD_MAX_SLOTS);  // ksplit does not depend on the slot count
   Workspace wsp(ws, ws_bytes);
   double* W = wsp.take<double>((size_t)round_up(N, BWD_BKR) * BWD_COEF_W);
-  double* part = wsp.take<double>((size_t)pl.ksplit * 2 * npad * npad);
+  double* part = wsp.take<double>((size_t)pl.kmax * 2 * npad * npad);
   if (!W || !part) return GDFT_WORKSPACE_TOO_SMALL;
   const int64_t Npad = round_up(N, BWD_BKR);
   for (int w = 0; w < Wn; w++) {

@@ -151,8 +151,9 @@ def _hf_fock_raw(basis: PackedBasis, g: torch.Tensor) -> torch.Tensor:
         raise TypeError(f"g must be [{basis.W}, 2, {basis.N}], got {tuple(g.shape)}")
     out = torch.empty((basis.W, 2, basis.n, basis.n), dtype=F64, device=basis.device)
     ws = workspace(L.gdft_workspace_bytes(_lib.OP_HF_FOCK, basis.N, basis.n, 0, basis.W), basis.device)
-    check(L.gdft_hf_fock(stream_ptr(), basis.N, basis.n, basis.W, basis.nplanes, ptr(basis.planes), ptr(basis.chi_packed), ptr(g),
-                         ptr(out), wptr(ws), ws.numel()), "gdft_hf_fock")
+    with _timed("gdft_hf_fock"):
+        check(L.gdft_hf_fock(stream_ptr(), basis.N, basis.n, basis.W, basis.nplanes, ptr(basis.planes), ptr(basis.chi_packed), ptr(g),
+                             ptr(out), wptr(ws), ws.numel()), "gdft_hf_fock")
     return out
 
 
@@ -160,6 +161,7 @@ class _DensityForward(Function):
     @staticmethod
     def forward(ctx, rdm1, basis, flags):
         ctx.basis, ctx.flags = basis, flags
+        ctx.set_materialize_grads(False)  # unused outputs (e.g. the stop_gradient'ed e_HF) must not cost a GEMM in the VJP
         return _density_fwd_raw(basis, rdm1, flags)
 
     @staticmethod
