@@ -2,6 +2,9 @@
 // The reverse pass evaluates the same template code on forward-mode dual numbers over the six local
 // variables (rho_a, rho_b, sigma_aa, sigma_bb, x_a, x_b) with x = laplacian (LYP) or tau (DM21 MGGA),
 // contracts with the output cotangent and applies d sigma_ss / d grad_rho_s = 2 grad_rho_s.
+// The reverse pass of the reverse pass (gdft_pointwise_bwd2: what differentiating V_xc once more needs, i.e.
+// training through the SCF loop, grad_dft/evaluate.py:917-1038) runs the same code on dual numbers whose
+// components are themselves dual numbers carrying the incoming direction.
 #include "common.cuh"
 #include "pointwise_math.h"
 
@@ -127,6 +130,81 @@ __global__ void __launch_bounds__(128) pointwise_bwd_kernel(const PwArgs a) {
   if (a.tau_bar) reinterpret_cast<double2*>(a.tau_bar)[r] = (needs & 4) ? make_double2(d[4], d[5]) : make_double2(0.0, 0.0);
 }
 
+// VJP of pointwise_bwd_kernel.  With X = (rho, grad_rho, x) the inputs, ob the output cotangent and
+// Xbar(X, ob) = J(X)^T ob the first-order result, this kernel receives the cotangent U of Xbar and returns
+//   ob_bar[f] = (J U)_f                      (a directional derivative: the inner dual part of the value)
+//   X_t       = d/dX <U, Xbar(X, ob)>        (mixed second derivatives: inner dual part of the outer derivatives,
+//                                             plus the explicit dependence of d sigma/d grad_rho on grad_rho)
+struct Pw2Args {
+  int64_t N;
+  double clip;
+  const double *rho, *grho, *tau, *lapl, *out_bar;
+  const double *u_rho, *u_grho, *u_tau, *u_lapl;
+  double *out_bar_bar, *rho_t, *grho_t, *tau_t, *lapl_t;
+};
+
+template <int ID>
+__global__ void __launch_bounds__(128) pointwise_bwd2_kernel(const Pw2Args a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.N) return;
+  constexpr int F = (ID == GDFT_PW_B88_SET || ID == GDFT_PW_DM21_GGA) ? 2 : (ID == GDFT_PW_B3LYP_SET || ID == GDFT_PW_DM21_MGGA) ? 4 : 1;
+  const int needs = pointwise_needs(ID);
+  typedef Dual<1> B1;
+  typedef Dual<6, B1> H;
+  const double2 rho = reinterpret_cast<const double2*>(a.rho)[r];
+  double g[6] = {0, 0, 0, 0, 0, 0}, ug[6] = {0, 0, 0, 0, 0, 0};
+  double x[6] = {rho.x, rho.y, 0, 0, 0, 0};
+  double w[6] = {0, 0, 0, 0, 0, 0};
+  if (a.u_rho) { const double2 u = reinterpret_cast<const double2*>(a.u_rho)[r]; w[0] = u.x; w[1] = u.y; }
+  if (needs & 1) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) g[q] = a.grho[r * 6 + q];
+    x[2] = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+    x[3] = g[3] * g[3] + g[4] * g[4] + g[5] * g[5];
+    if (a.u_grho) {
+#pragma unroll
+      for (int q = 0; q < 6; q++) ug[q] = a.u_grho[r * 6 + q];
+      w[2] = 2.0 * (g[0] * ug[0] + g[1] * ug[1] + g[2] * ug[2]);
+      w[3] = 2.0 * (g[3] * ug[3] + g[4] * ug[4] + g[5] * ug[5]);
+    }
+  }
+  if (needs & 2) {
+    const double2 l = reinterpret_cast<const double2*>(a.lapl)[r]; x[4] = l.x; x[5] = l.y;
+    if (a.u_lapl) { const double2 u = reinterpret_cast<const double2*>(a.u_lapl)[r]; w[4] = u.x; w[5] = u.y; }
+  }
+  if (needs & 4) {
+    const double2 l = reinterpret_cast<const double2*>(a.tau)[r]; x[4] = l.x; x[5] = l.y;
+    if (a.u_tau) { const double2 u = reinterpret_cast<const double2*>(a.u_tau)[r]; w[4] = u.x; w[5] = u.y; }
+  }
+  H v[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    B1 b; b.v = x[q]; b.d[0] = w[q];
+    v[q] = pw::Make<H>::variable(b, q);
+  }
+  H feats[F];
+  eval_features<ID, H>(v, a.clip, feats);
+  double d[6] = {0, 0, 0, 0, 0, 0}, h[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int f = 0; f < F; f++) {
+    const double ob = a.out_bar[r * F + f];
+    if (a.out_bar_bar) a.out_bar_bar[r * F + f] = feats[f].v.d[0];
+#pragma unroll
+    for (int q = 0; q < 6; q++) { d[q] = fma(ob, feats[f].d[q].v, d[q]); h[q] = fma(ob, feats[f].d[q].d[0], h[q]); }
+  }
+  if (a.rho_t) reinterpret_cast<double2*>(a.rho_t)[r] = make_double2(h[0], h[1]);
+  if (a.grho_t) {
+    double* o = a.grho_t + r * 6;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      o[j] = 2.0 * (h[2] * g[j] + d[2] * ug[j]);
+      o[3 + j] = 2.0 * (h[3] * g[3 + j] + d[3] * ug[3 + j]);
+    }
+  }
+  if (a.lapl_t) reinterpret_cast<double2*>(a.lapl_t)[r] = (needs & 2) ? make_double2(h[4], h[5]) : make_double2(0.0, 0.0);
+  if (a.tau_t) reinterpret_cast<double2*>(a.tau_t)[r] = (needs & 4) ? make_double2(h[4], h[5]) : make_double2(0.0, 0.0);
+}
+
 // functional.py:520-531: [rho'_a, rho'_b, |g_a+g_b|^2, |g_a|^2, |g_b|^2, tau_a, tau_b], rho' = max(|rho|,clip) sign(rho)
 __global__ void __launch_bounds__(128) dm21_inputs_fwd_kernel(const PwArgs a) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,6 +240,70 @@ __global__ void __launch_bounds__(128) dm21_inputs_bwd_kernel(const PwArgs a) {
   }
   if (a.tau_bar) reinterpret_cast<double2*>(a.tau_bar)[r] = make_double2(ob[5], ob[6]);
   if (a.lapl_bar) reinterpret_cast<double2*>(a.lapl_bar)[r] = make_double2(0.0, 0.0);
+}
+
+// VJP of dm21_inputs_bwd_kernel: the squash derivative is piecewise constant and the gradient columns are quadratic
+// forms, so only the (grad_rho, out_bar) cross terms survive.
+__global__ void __launch_bounds__(128) dm21_inputs_bwd2_kernel(const Pw2Args a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.N) return;
+  const double2 rho = reinterpret_cast<const double2*>(a.rho)[r];
+  const double* g = a.grho + r * 6;
+  const double* ob = a.out_bar + r * 7;
+  auto dsq = [&](double x) { const double ax = fabs(x); return ax > a.clip ? 1.0 : (ax == a.clip ? 0.5 : 0.0); };
+  double ur[2] = {0, 0}, ug[6] = {0, 0, 0, 0, 0, 0}, ut[2] = {0, 0};
+  if (a.u_rho) { const double2 u = reinterpret_cast<const double2*>(a.u_rho)[r]; ur[0] = u.x; ur[1] = u.y; }
+  if (a.u_grho)
+    for (int q = 0; q < 6; q++) ug[q] = a.u_grho[r * 6 + q];
+  if (a.u_tau) { const double2 u = reinterpret_cast<const double2*>(a.u_tau)[r]; ut[0] = u.x; ut[1] = u.y; }
+  if (a.out_bar_bar) {
+    double* o = a.out_bar_bar + r * 7;
+    double st = 0, sa = 0, sb = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      st += 2.0 * (g[j] + g[3 + j]) * (ug[j] + ug[3 + j]);
+      sa += 2.0 * g[j] * ug[j];
+      sb += 2.0 * g[3 + j] * ug[3 + j];
+    }
+    o[0] = dsq(rho.x) * ur[0]; o[1] = dsq(rho.y) * ur[1];
+    o[2] = st; o[3] = sa; o[4] = sb; o[5] = ut[0]; o[6] = ut[1];
+  }
+  if (a.rho_t) reinterpret_cast<double2*>(a.rho_t)[r] = make_double2(0.0, 0.0);
+  if (a.grho_t) {
+    double* o = a.grho_t + r * 6;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double t = 2.0 * ob[2] * (ug[j] + ug[3 + j]);
+      o[j] = t + 2.0 * ob[3] * ug[j];
+      o[3 + j] = t + 2.0 * ob[4] * ug[3 + j];
+    }
+  }
+  if (a.tau_t) reinterpret_cast<double2*>(a.tau_t)[r] = make_double2(0.0, 0.0);
+  if (a.lapl_t) reinterpret_cast<double2*>(a.lapl_t)[r] = make_double2(0.0, 0.0);
+}
+
+template <int ID>
+static void launch_pw2(cudaStream_t st, const Pw2Args& a) {
+  pointwise_bwd2_kernel<ID><<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a);
+}
+
+static int dispatch_pw2(cudaStream_t st, int id, const Pw2Args& a) {
+  switch (id) {
+    case GDFT_PW_LSDA_X: launch_pw2<GDFT_PW_LSDA_X>(st, a); break;
+    case GDFT_PW_B88_X: launch_pw2<GDFT_PW_B88_X>(st, a); break;
+    case GDFT_PW_VWN_C: launch_pw2<GDFT_PW_VWN_C>(st, a); break;
+    case GDFT_PW_LYP_C: launch_pw2<GDFT_PW_LYP_C>(st, a); break;
+    case GDFT_PW_PW92_C: launch_pw2<GDFT_PW_PW92_C>(st, a); break;
+    case GDFT_PW_B3LYP_SET: launch_pw2<GDFT_PW_B3LYP_SET>(st, a); break;
+    case GDFT_PW_B88_SET: launch_pw2<GDFT_PW_B88_SET>(st, a); break;
+    case GDFT_PW_DM21_LDA: launch_pw2<GDFT_PW_DM21_LDA>(st, a); break;
+    case GDFT_PW_DM21_GGA: launch_pw2<GDFT_PW_DM21_GGA>(st, a); break;
+    case GDFT_PW_DM21_MGGA: launch_pw2<GDFT_PW_DM21_MGGA>(st, a); break;
+    case GDFT_PW_DM21_INPUTS: dm21_inputs_bwd2_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a); break;
+    default: return GDFT_BAD_ARGUMENT;
+  }
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
 }
 
 template <int ID>
@@ -230,4 +372,20 @@ extern "C" int gdft_pointwise_bwd(gdft_stream_t stream, int64_t N, int id, doubl
   a.N = N; a.clip = clip; a.rho = rho; a.grho = grad_rho; a.tau = tau; a.lapl = lapl; a.out_bar = out_bar;
   a.rho_bar = rho_bar; a.grho_bar = grad_rho_bar; a.tau_bar = tau_bar; a.lapl_bar = lapl_bar;
   return dispatch_pw(true, static_cast<cudaStream_t>(stream), id, a);
+}
+
+extern "C" int gdft_pointwise_bwd2(gdft_stream_t stream, int64_t N, int id, double clip, const double* rho, const double* grad_rho,
+                                   const double* tau, const double* lapl, const double* out_bar, const double* u_rho,
+                                   const double* u_grad_rho, const double* u_tau, const double* u_lapl, double* out_bar_bar,
+                                   double* rho_t, double* grad_rho_t, double* tau_t, double* lapl_t) {
+  int rc = check_pw_inputs(N, id, rho, grad_rho, tau, lapl);
+  if (rc) return rc;
+  if (!out_bar) return GDFT_BAD_ARGUMENT;
+  if (!aligned16(u_rho) || !aligned16(u_tau) || !aligned16(u_lapl) || !aligned16(rho_t) || !aligned16(tau_t) || !aligned16(lapl_t))
+    return GDFT_BAD_ALIGNMENT;
+  Pw2Args a{};
+  a.N = N; a.clip = clip; a.rho = rho; a.grho = grad_rho; a.tau = tau; a.lapl = lapl; a.out_bar = out_bar;
+  a.u_rho = u_rho; a.u_grho = u_grad_rho; a.u_tau = u_tau; a.u_lapl = u_lapl;
+  a.out_bar_bar = out_bar_bar; a.rho_t = rho_t; a.grho_t = grad_rho_t; a.tau_t = tau_t; a.lapl_t = lapl_t;
+  return dispatch_pw2(static_cast<cudaStream_t>(stream), id, a);
 }

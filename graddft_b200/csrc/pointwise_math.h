@@ -26,89 +26,94 @@ namespace pw {
 constexpr double LN2 = 0.693147180559945309417232121458;
 constexpr double PI = 3.14159265358979323846264338328;
 
-template <int NV>
+// Forward-mode dual number over a base scalar B: B = double gives first derivatives; B = Dual<1> (itself a dual
+// number carrying one direction) gives, in addition, the derivative of every first derivative along that
+// direction -- what the VJP of the VJP needs (training through the SCF loop differentiates V_xc once more).
+template <int NV, typename B = double>
 struct Dual {
-  double v;
-  double d[NV];
+  B v;
+  B d[NV];
 };
 
 // ---- construction ---------------------------------------------------------------------------------
 template <typename T> struct Make;
 template <> struct Make<double> {
   static GDFT_HD double constant(double c) { return c; }
-  static GDFT_HD double variable(double x, int) { return x; }
 };
-template <int NV> struct Make<Dual<NV>> {
-  static GDFT_HD Dual<NV> constant(double c) {
-    Dual<NV> r; r.v = c;
+template <int NV, typename B> struct Make<Dual<NV, B>> {
+  static GDFT_HD Dual<NV, B> constant(double c) {
+    Dual<NV, B> r; r.v = Make<B>::constant(c);
 #pragma unroll
-    for (int i = 0; i < NV; i++) r.d[i] = 0.0;
+    for (int i = 0; i < NV; i++) r.d[i] = Make<B>::constant(0.0);
     return r;
   }
-  static GDFT_HD Dual<NV> variable(double x, int idx) {
-    Dual<NV> r; r.v = x;
+  static GDFT_HD Dual<NV, B> variable(const B& x, int idx) {
+    Dual<NV, B> r; r.v = x;
 #pragma unroll
-    for (int i = 0; i < NV; i++) r.d[i] = (i == idx) ? 1.0 : 0.0;
+    for (int i = 0; i < NV; i++) r.d[i] = Make<B>::constant((i == idx) ? 1.0 : 0.0);
     return r;
   }
 };
 
 GDFT_HD double val(double x) { return x; }
-template <int NV> GDFT_HD double val(const Dual<NV>& x) { return x.v; }
+template <int NV, typename B> GDFT_HD double val(const Dual<NV, B>& x) { return val(x.v); }
 
-// chain rule helper: f(x) with value fv and derivative fd
-template <int NV> GDFT_HD Dual<NV> chain(const Dual<NV>& x, double fv, double fd) {
-  Dual<NV> r; r.v = fv;
+// chain rule helper: f(x) with value fv and derivative fd (both of the base type)
+template <int NV, typename B> GDFT_HD Dual<NV, B> chain(const Dual<NV, B>& x, const B& fv, const B& fd) {
+  Dual<NV, B> r; r.v = fv;
 #pragma unroll
   for (int i = 0; i < NV; i++) r.d[i] = fd * x.d[i];
   return r;
 }
 
 // ---- arithmetic -----------------------------------------------------------------------------------
-template <int NV> GDFT_HD Dual<NV> operator+(const Dual<NV>& a, const Dual<NV>& b) {
-  Dual<NV> r; r.v = a.v + b.v;
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator+(const Dual<NV, B>& a, const Dual<NV, B>& b) {
+  Dual<NV, B> r; r.v = a.v + b.v;
 #pragma unroll
   for (int i = 0; i < NV; i++) r.d[i] = a.d[i] + b.d[i];
   return r;
 }
-template <int NV> GDFT_HD Dual<NV> operator-(const Dual<NV>& a, const Dual<NV>& b) {
-  Dual<NV> r; r.v = a.v - b.v;
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator-(const Dual<NV, B>& a, const Dual<NV, B>& b) {
+  Dual<NV, B> r; r.v = a.v - b.v;
 #pragma unroll
   for (int i = 0; i < NV; i++) r.d[i] = a.d[i] - b.d[i];
   return r;
 }
-template <int NV> GDFT_HD Dual<NV> operator*(const Dual<NV>& a, const Dual<NV>& b) {
-  Dual<NV> r; r.v = a.v * b.v;
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator*(const Dual<NV, B>& a, const Dual<NV, B>& b) {
+  Dual<NV, B> r; r.v = a.v * b.v;
 #pragma unroll
   for (int i = 0; i < NV; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
   return r;
 }
-template <int NV> GDFT_HD Dual<NV> operator/(const Dual<NV>& a, const Dual<NV>& b) {
-  Dual<NV> r; r.v = a.v / b.v;
-  const double inv = 1.0 / b.v;
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator/(const Dual<NV, B>& a, const Dual<NV, B>& b) {
+  Dual<NV, B> r; r.v = a.v / b.v;
+  const B inv = 1.0 / b.v;
 #pragma unroll
   for (int i = 0; i < NV; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
   return r;
 }
-template <int NV> GDFT_HD Dual<NV> operator-(const Dual<NV>& a) {
-  Dual<NV> r; r.v = -a.v;
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator-(const Dual<NV, B>& a) {
+  Dual<NV, B> r; r.v = -a.v;
 #pragma unroll
   for (int i = 0; i < NV; i++) r.d[i] = -a.d[i];
   return r;
 }
-template <int NV> GDFT_HD Dual<NV> operator+(const Dual<NV>& a, double c) { Dual<NV> r = a; r.v += c; return r; }
-template <int NV> GDFT_HD Dual<NV> operator+(double c, const Dual<NV>& a) { return a + c; }
-template <int NV> GDFT_HD Dual<NV> operator-(const Dual<NV>& a, double c) { Dual<NV> r = a; r.v -= c; return r; }
-template <int NV> GDFT_HD Dual<NV> operator-(double c, const Dual<NV>& a) { return (-a) + c; }
-template <int NV> GDFT_HD Dual<NV> operator*(const Dual<NV>& a, double c) {
-  Dual<NV> r; r.v = a.v * c;
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator+(const Dual<NV, B>& a, double c) { Dual<NV, B> r = a; r.v = r.v + c; return r; }
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator+(double c, const Dual<NV, B>& a) { return a + c; }
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator-(const Dual<NV, B>& a, double c) { Dual<NV, B> r = a; r.v = r.v - c; return r; }
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator-(double c, const Dual<NV, B>& a) { return (-a) + c; }
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator*(const Dual<NV, B>& a, double c) {
+  Dual<NV, B> r; r.v = a.v * c;
 #pragma unroll
   for (int i = 0; i < NV; i++) r.d[i] = a.d[i] * c;
   return r;
 }
-template <int NV> GDFT_HD Dual<NV> operator*(double c, const Dual<NV>& a) { return a * c; }
-template <int NV> GDFT_HD Dual<NV> operator/(const Dual<NV>& a, double c) { return a * (1.0 / c); }
-template <int NV> GDFT_HD Dual<NV> operator/(double c, const Dual<NV>& a) { return chain(a, c / a.v, -c / (a.v * a.v)); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator*(double c, const Dual<NV, B>& a) { return a * c; }
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator/(const Dual<NV, B>& a, double c) { return a * (1.0 / c); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> operator/(double c, const Dual<NV, B>& a) {
+  const B q = c / a.v;
+  return chain(a, q, -(q / a.v));
+}
 
 // ---- elementary functions (double overloads first) --------------------------------------------------
 GDFT_HD double f_log2(double x) { return log2(x); }
@@ -122,25 +127,33 @@ GDFT_HD double f_pow(double x, double p) { return pow(x, p); }
 GDFT_HD double f_clip_min(double x, double c) { return x >= c ? x : c; }
 GDFT_HD double f_select(bool cond, double a, double b) { return cond ? a : b; }
 
-template <int NV> GDFT_HD Dual<NV> f_log2(const Dual<NV>& x) { return chain(x, log2(x.v), 1.0 / (x.v * LN2)); }
-template <int NV> GDFT_HD Dual<NV> f_exp2(const Dual<NV>& x) { const double e = exp2(x.v); return chain(x, e, e * LN2); }
-template <int NV> GDFT_HD Dual<NV> f_log(const Dual<NV>& x) { return chain(x, log(x.v), 1.0 / x.v); }
-template <int NV> GDFT_HD Dual<NV> f_exp(const Dual<NV>& x) { const double e = exp(x.v); return chain(x, e, e); }
-template <int NV> GDFT_HD Dual<NV> f_sqrt(const Dual<NV>& x) { const double s = sqrt(x.v); return chain(x, s, 0.5 / s); }
-template <int NV> GDFT_HD Dual<NV> f_atan(const Dual<NV>& x) { return chain(x, atan(x.v), 1.0 / (1.0 + x.v * x.v)); }
-template <int NV> GDFT_HD Dual<NV> f_asinh(const Dual<NV>& x) { return chain(x, asinh(x.v), 1.0 / sqrt(1.0 + x.v * x.v)); }
-template <int NV> GDFT_HD Dual<NV> f_pow(const Dual<NV>& x, double p) { return chain(x, pow(x.v, p), p * pow(x.v, p - 1.0)); }
+// Each derivative is written in base-type arithmetic, so that with B = Dual<1> it is itself differentiated.
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_log2(const Dual<NV, B>& x) { return chain(x, f_log2(x.v), (1.0 / LN2) / x.v); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_exp2(const Dual<NV, B>& x) { const B e = f_exp2(x.v); return chain(x, e, e * LN2); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_log(const Dual<NV, B>& x) { return chain(x, f_log(x.v), 1.0 / x.v); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_exp(const Dual<NV, B>& x) { const B e = f_exp(x.v); return chain(x, e, e); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_sqrt(const Dual<NV, B>& x) { const B s = f_sqrt(x.v); return chain(x, s, 0.5 / s); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_atan(const Dual<NV, B>& x) { return chain(x, f_atan(x.v), 1.0 / (1.0 + x.v * x.v)); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_asinh(const Dual<NV, B>& x) { return chain(x, f_asinh(x.v), 1.0 / f_sqrt(1.0 + x.v * x.v)); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_pow(const Dual<NV, B>& x, double p) { return chain(x, f_pow(x.v, p), p * f_pow(x.v, p - 1.0)); }
 // jnp.clip(x, a_min=c): value max(x,c); derivative passes where x >= c (torch.clamp convention at the tie)
-template <int NV> GDFT_HD Dual<NV> f_clip_min(const Dual<NV>& x, double c) { return x.v >= c ? x : Make<Dual<NV>>::constant(c); }
-template <int NV> GDFT_HD Dual<NV> f_select(bool cond, const Dual<NV>& a, const Dual<NV>& b) { return cond ? a : b; }
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_clip_min(const Dual<NV, B>& x, double c) {
+  return val(x) >= c ? x : Make<Dual<NV, B>>::constant(c);
+}
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_select(bool cond, const Dual<NV, B>& a, const Dual<NV, B>& b) { return cond ? a : b; }
 
 // 2^(4 log2(x) / 3), the reference's log-domain x^{4/3} (functional.py:1014-1016).  Value exactly as written
 // there; derivative (4/3) x^{1/3}, which stays finite (0) at x == 0 where differentiating through log2
-// would give 0 * inf (fully spin-polarised points).
+// would give 0 * inf (fully spin-polarised points).  One level further down (the derivative of that derivative,
+// (4/9) x^{-2/3}, is infinite at x == 0) the exact-zero point is treated as a constant.
 GDFT_HD double f_pow43_log2(double x) { return exp2(4.0 * log2(x) / 3.0); }
-template <int NV> GDFT_HD Dual<NV> f_pow43_log2(const Dual<NV>& x) {
-  const double l = log2(x.v);
-  return chain(x, exp2(4.0 * l / 3.0), (4.0 / 3.0) * exp2(l / 3.0));
+GDFT_HD double f_cbrt43(double x) { return (4.0 / 3.0) * exp2(log2(x) / 3.0); }
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_cbrt43(const Dual<NV, B>& x) {
+  if (val(x) == 0.0) return Make<Dual<NV, B>>::constant(0.0);
+  return chain(x, f_cbrt43(x.v), (4.0 / 9.0) * f_exp2(-2.0 * f_log2(x.v) / 3.0));
+}
+template <int NV, typename B> GDFT_HD Dual<NV, B> f_pow43_log2(const Dual<NV, B>& x) {
+  return chain(x, f_pow43_log2(x.v), f_cbrt43(x.v));
 }
 
 template <typename T> GDFT_HD T cst(double c) { return Make<T>::constant(c); }

@@ -143,6 +143,7 @@ def diff_scf_loop(functional: Functional, cycles: int = 25, **kwargs) -> Callabl
     """grad_dft/evaluate.py:917-1038: differentiable DIIS SCF loop.  Returns `iterator(params, molecule) -> Molecule`
     whose `.energy` is the prediction after `cycles` iterations."""
     kwargs.pop("chunk_size", None)
+    kwargs.setdefault("differentiable_fock", True)  # jax.grad of the loop differentiates every Fock build (evaluate.py:917)
     compute_energy = energy_predictor(functional, **kwargs)
 
     def scf_jitted_iterator(params, molecule: Molecule, *args) -> Molecule:
@@ -174,6 +175,7 @@ def diff_scf_loop(functional: Functional, cycles: int = 25, **kwargs) -> Callabl
 def diff_simple_scf_loop(functional: Functional, cycles: int = 25, mixing_factor: float = 0.4, **kwargs) -> Callable:
     """grad_dft/evaluate.py:257-352: differentiable SCF loop with linear density mixing."""
     kwargs.pop("chunk_size", None)
+    kwargs.setdefault("differentiable_fock", True)
     compute_energy = energy_predictor(functional, **kwargs)
 
     def simple_scf_jitted_iterator(params, atoms: Molecule, *args) -> Molecule:

@@ -122,10 +122,11 @@ def HF_density_grad_2_Fock(grid, functional, params, chi: Array, ao: Array, ehf:
     """grad_dft/molecule.py:545-613: g = dE_xc/d e_HF through the densities, then F[w,s] = -1/2 ao^T diag(g) chi.
     `chunk_size` is accepted and ignored (the GEMM kernel needs no chunking).  Returns [omega, spin, n, n]."""
     ehf_leaf = ehf.detach().requires_grad_(True)
+    higher = torch.is_grad_enabled()  # under a differentiable SCF loop g itself depends on params / the features
     with torch.enable_grad():
         densities = functional.combine_densities(densities_wout_hf, ehf_leaf)
         e = functional.xc_energy(params, grid, coefficient_inputs, densities)
-    (gr,) = torch.autograd.grad(e, ehf_leaf)
+    (gr,) = torch.autograd.grad(e, ehf_leaf, create_graph=higher)
     basis = _basis if _basis is not None else _CACHE.get(ao, chi=chi)
     return ops.hf_fock(basis, gr)
 
@@ -134,10 +135,11 @@ def HF_coefficient_input_grad_2_Fock(grid, functional, params, chi: Array, ao: A
                                      densities: Array, chunk_size=None, precision=None, _basis=None) -> Array:
     """grad_dft/molecule.py:617-685: same as above with the derivative taken through the coefficient inputs."""
     ehf_leaf = ehf.detach().requires_grad_(True)
+    higher = torch.is_grad_enabled()
     with torch.enable_grad():
         cinputs = functional.combine_inputs(cinputs_wout_hf, ehf_leaf)
         e = functional.xc_energy(params, grid, cinputs, densities)
-    (gr,) = torch.autograd.grad(e, ehf_leaf)
+    (gr,) = torch.autograd.grad(e, ehf_leaf, create_graph=higher)
     basis = _basis if _basis is not None else _CACHE.get(ao, chi=chi)
     return ops.hf_fock(basis, gr)
 

@@ -420,27 +420,63 @@ class _Pointwise(Function):
         return out
 
     @staticmethod
-    @once_differentiable  # the per-point VJP kernel is first-order: differentiating through it raises instead of silently dropping terms
     def backward(ctx, out_bar):
+        saved = list(ctx.saved_tensors)
+        rho = saved.pop(0)
+        grho = saved.pop(0) if ctx.present[0] else None
+        tau = saved.pop(0) if ctx.present[1] else None
+        lapl = saved.pop(0) if ctx.present[2] else None
+        rb, gb, tb, lb = _PointwiseVJP.apply(ctx.pw_id, ctx.clip, rho, grho, tau, lapl, out_bar)
+        need = ctx.needs_input_grad
+        return None, None, rb if need[2] else None, gb if need[3] else None, tb if need[4] else None, lb if need[5] else None
+
+
+class _PointwiseVJP(Function):
+    """(rho, grad_rho, tau, lapl, out_bar) -> input cotangents (gdft_pointwise_bwd); differentiable once more through
+    gdft_pointwise_bwd2, which is what training through the SCF loop (grad of a function of V_xc) needs."""
+
+    @staticmethod
+    def forward(ctx, pw_id, clip, rho, grho, tau, lapl, out_bar):
+        L = lib()
+        out_bar = _c(out_bar)
+        N = int(rho.shape[0])
+        rb = torch.empty_like(rho)
+        gb = torch.empty_like(grho) if grho is not None else None
+        tb = torch.empty_like(tau) if tau is not None else None
+        lb = torch.empty_like(lapl) if lapl is not None else None
+        check(L.gdft_pointwise_bwd(stream_ptr(), N, pw_id, clip, ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(out_bar),
+                                   ptr(rb), ptr(gb), ptr(tb), ptr(lb)), "gdft_pointwise_bwd")
+        ctx.pw_id, ctx.clip = pw_id, clip
+        ctx.present = (grho is not None, tau is not None, lapl is not None)
+        ctx.save_for_backward(*[t for t in (rho, grho, tau, lapl, out_bar) if t is not None])
+        ctx.set_materialize_grads(False)
+        return rb, gb, tb, lb
+
+    @staticmethod
+    @once_differentiable  # third order is not bound: differentiating through this raises instead of silently dropping terms
+    def backward(ctx, u_rho, u_grho, u_tau, u_lapl):
         L = lib()
         saved = list(ctx.saved_tensors)
         rho = saved.pop(0)
         grho = saved.pop(0) if ctx.present[0] else None
         tau = saved.pop(0) if ctx.present[1] else None
         lapl = saved.pop(0) if ctx.present[2] else None
+        out_bar = saved.pop(0)
         N = int(rho.shape[0])
         need = ctx.needs_input_grad
-        rb = torch.empty_like(rho) if need[2] else None
-        gb = torch.empty_like(grho) if (grho is not None and need[3]) else None
-        tb = torch.empty_like(tau) if (tau is not None and need[4]) else None
-        lb = torch.empty_like(lapl) if (lapl is not None and need[5]) else None
-        check(L.gdft_pointwise_bwd(stream_ptr(), N, ctx.pw_id, ctx.clip, ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(_c(out_bar)),
-                                   ptr(rb), ptr(gb), ptr(tb), ptr(lb)), "gdft_pointwise_bwd")
-        return None, None, rb, gb, tb, lb
+        rt = torch.empty_like(rho) if need[2] else None
+        gt = torch.empty_like(grho) if (grho is not None and need[3]) else None
+        tt = torch.empty_like(tau) if (tau is not None and need[4]) else None
+        lt = torch.empty_like(lapl) if (lapl is not None and need[5]) else None
+        obb = torch.empty_like(out_bar) if need[6] else None
+        check(L.gdft_pointwise_bwd2(stream_ptr(), N, ctx.pw_id, ctx.clip, ptr(rho), ptr(grho), ptr(tau), ptr(lapl), ptr(out_bar),
+                                    ptr(_c(u_rho)), ptr(_c(u_grho)), ptr(_c(u_tau)), ptr(_c(u_lapl)),
+                                    ptr(obb), ptr(rt), ptr(gt), ptr(tt), ptr(lt)), "gdft_pointwise_bwd2")
+        return None, None, rt, gt, tt, lt, obb
 
 
 def pointwise(name: str, rho, grad_rho=None, tau=None, lapl=None, clip: float = 1e-30) -> torch.Tensor:
-    """out[N,F] of one closed-form feature set (see _lib.PW_IDS); first-order differentiable."""
+    """out[N,F] of one closed-form feature set (see _lib.PW_IDS); differentiable to second order."""
     return _Pointwise.apply(_lib.PW_IDS[name], clip, rho, grad_rho, tau, lapl)
 
 

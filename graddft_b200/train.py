@@ -36,7 +36,9 @@ def xc_energy_and_grads(functional: Functional, params, rdm1: Array, atoms: Mole
     carrying the differentiated rdm1 (its cached grid quantities are reused by the hybrid terms)."""
     keep_exc_graph = torch.is_grad_enabled() and (_requires_grad(params) or rdm1.requires_grad)
     if create_graph is None:
-        create_graph = False  # V_xc differentiable w.r.t. params/rdm1 needs second-order per-point kernels (not bound yet)
+        # V_xc itself differentiable (w.r.t. params and rdm1) only when the density matrix already carries a graph,
+        # i.e. inside a differentiable SCF loop (evaluate.py:917-1038); energy-only losses need first order only
+        create_graph = torch.is_grad_enabled() and rdm1.requires_grad
     leaf = rdm1 if (create_graph and rdm1.requires_grad) else rdm1.detach().requires_grad_(True)
     with torch.enable_grad():
         at = atoms.replace(rdm1=leaf)
@@ -49,8 +51,11 @@ def xc_energy_and_grads(functional: Functional, params, rdm1: Array, atoms: Mole
     return exc, fock_xc, at
 
 
-def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: float = 1e-30, **kwargs) -> Callable:
-    """grad_dft/train.py:34-218."""
+def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: float = 1e-30, differentiable_fock: Optional[bool] = None,
+                     **kwargs) -> Callable:
+    """grad_dft/train.py:34-218.  `differentiable_fock` (not upstream, where jax traces everything): True keeps the
+    returned Fock matrix differentiable w.r.t. params and rdm1 (second-order kernels; what `diff_scf_loop` asks for
+    when params require grad), False never does, None = only when rdm1 already carries a graph."""
     if nlc_functional is not None:
         raise NotImplementedError("nlc_functional: the reference path raises NameError here (train.py:117-120)")
 
@@ -85,19 +90,24 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
             else:
                 cinputs, grad_cinputs, nograd_cinputs = None, None, None
 
-        def detached(t):
-            return t.detach() if isinstance(t, torch.Tensor) else t
+            # first order: the features enter the explicit terms as constants; differentiable Fock: they keep their
+            # graph, as under jax.grad of the whole loop (train.py:200-213 passes them un-stopped)
+            def through(t):
+                return t if (differentiable or not isinstance(t, torch.Tensor)) else t.detach()
 
-        terms = []
-        if functional.densitygrads:
-            terms.append(functional.densitygrads(functional, params, at, nograd_densities, detached(cinputs), detached(grad_densities)))
-        if functional.coefficient_input_grads:
-            terms.append(functional.coefficient_input_grads(functional, params, at, nograd_cinputs, detached(grad_cinputs), detached(densities)))
+            terms = []
+            if functional.densitygrads:
+                terms.append(functional.densitygrads(functional, params, at, nograd_densities, through(cinputs), through(grad_densities)))
+            if functional.coefficient_input_grads:
+                terms.append(functional.coefficient_input_grads(functional, params, at, nograd_cinputs, through(grad_cinputs), through(densities)))
         return terms
 
     def predict(params, atoms: Molecule, *args) -> Tuple[Array, Array]:
         shard = atoms.__dict__.get("_shard")
-        exc, fock_xc, at = xc_energy_and_grads(functional, params, atoms.rdm1, atoms, *args)
+        create_graph = differentiable_fock
+        if differentiable_fock and not (torch.is_grad_enabled() and (_requires_grad(params) or atoms.rdm1.requires_grad)):
+            create_graph = False
+        exc, fock_xc, at = xc_energy_and_grads(functional, params, atoms.rdm1, atoms, *args, create_graph=create_graph)
         differentiable = fock_xc.requires_grad
         P = atoms.rdm1.sum(dim=0)
         if shard is not None:

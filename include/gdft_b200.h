@@ -168,6 +168,14 @@ int gdft_pointwise_bwd(gdft_stream_t stream, int64_t N, int id, double clip, con
                        const double* out_bar, double* rho_bar, double* grad_rho_bar, double* tau_bar,
                        double* lapl_bar);
 
+/* VJP of gdft_pointwise_bwd (second order: differentiating V_xc once more, i.e. training through the SCF loop,
+ * grad_dft/evaluate.py:917-1038 under jax.grad).  u_* are the cotangents of gdft_pointwise_bwd's outputs (NULL = zero);
+ * out_bar_bar[N,F] is the cotangent of out_bar, *_t those of the inputs.  Outputs may be NULL. */
+int gdft_pointwise_bwd2(gdft_stream_t stream, int64_t N, int id, double clip, const double* rho,
+                        const double* grad_rho, const double* tau, const double* lapl, const double* out_bar,
+                        const double* u_rho, const double* u_grad_rho, const double* u_tau, const double* u_lapl,
+                        double* out_bar_bar, double* rho_t, double* grad_rho_t, double* tau_t, double* lapl_t);
+
 /* ---- predictor glue ----------------------------------------------------------------------------
  * fock = aclip(1/2 (X + X^T)), X = aclip(h1e + J + Dbar)   (grad_dft/train.py:148-163) */
 int gdft_fock_assemble(gdft_stream_t stream, int64_t n, const double* h1e, const double* J,

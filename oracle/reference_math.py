@@ -28,6 +28,7 @@ __all__ = [
     "dm21_mlp", "dm21_mlp_init", "mgga_feature_densities",
     "xc_energy_of_rdm1", "predict_b3lyp", "predict_semilocal", "predict_dm21",
     "density_vjp_formula", "safe_fock_solver", "jittable_diis_run", "diff_scf_loop_energy",
+    "predict_dm21_traced", "diff_simple_scf_loop_energy",
 ]
 
 
@@ -539,6 +540,51 @@ def predict_dm21(mol: dict, params, clip: float = CLIP):
     v = HF_fock(chi, g, ao).sum(dim=0)
     fock = abs_clip(fock + (v + v.transpose(1, 2)), clip)  # train.py:205,212: fock += V + V^T
     return energy, abs_clip(fock, clip)
+
+
+def predict_dm21_traced(mol: dict, params, clip: float = CLIP):
+    """train.py:147-216 for a DM21-shaped functional as `jax.grad` of an enclosing function sees it: every
+    intermediate keeps its dependence on (params, mol["rdm1"]) -- V_xc is itself differentiable (create_graph), the
+    features passed to the explicit HF routes are NOT stopped (train.py:200-213) -- except what the reference wraps
+    in stop_gradient (the HF energy density entering E_xc, functional.py:176,203, and the `ehf` argument of the two
+    HF routes).  Used to check gradients through the SCF loops (evaluate.py:257-352, 917-1038)."""
+    D = mol["rdm1"] if mol["rdm1"].requires_grad else mol["rdm1"].detach().clone().requires_grad_(True)
+    Exc = xc_energy_of_rdm1(D, mol, "DM21", params=params, clip=clip)
+    (fock_xc,) = torch.autograd.grad(Exc, D, create_graph=True)
+    P = D.sum(dim=0)
+    energy = Exc + nonXC(P, mol["h1e"], mol["rep_tensor"], mol["nuclear_repulsion"])
+    fock = _fock_common(D, mol, fock_xc, clip)
+    ao, gao, chi, w = mol["ao"], mol["grad_ao"], mol["chi"], mol["weights"]
+    rho, grho, tau = density(D, ao), grad_density(D, ao, gao), kinetic_density(D, gao)
+    grad_densities = dm21_densities(rho, grho, tau, "LDA", clip)
+    grad_cinputs = dm21_coefficient_inputs(rho, grho, tau, clip)
+    ehf0 = HF_energy_density(D, ao, chi).detach()
+    densities = dm21_combine_densities(grad_densities, ehf0)
+    cinputs = dm21_combine_cinputs(grad_cinputs, ehf0)
+    ehf = ehf0.clone().requires_grad_(True)
+    E = xc_energy(dm21_mlp(params, cinputs), dm21_combine_densities(grad_densities, ehf), w, clip)
+    (g,) = torch.autograd.grad(E, ehf, create_graph=True)
+    v = HF_fock(chi, g, ao).sum(dim=0)
+    fock = abs_clip(fock + (v + v.transpose(1, 2)), clip)
+    ehf = ehf0.clone().requires_grad_(True)
+    E = xc_energy(dm21_mlp(params, dm21_combine_cinputs(grad_cinputs, ehf)), densities, w, clip)
+    (g,) = torch.autograd.grad(E, ehf, create_graph=True)
+    v = HF_fock(chi, g, ao).sum(dim=0)
+    fock = abs_clip(fock + (v + v.transpose(1, 2)), clip)
+    return energy, abs_clip(fock, clip)
+
+
+def diff_simple_scf_loop_energy(mol: dict, predict: Callable, cycles: int, mixing_factor: float = 0.4):
+    """evaluate.py:300-350 -- linear density mixing; differentiable when `predict` is traced."""
+    mol = dict(mol)
+    e, fock = predict(mol)
+    nelecs = mol["mo_occ"].sum(dim=1).round().to(torch.int64)
+    for _ in range(cycles):
+        mo_energy, mo_coeff = safe_fock_solver(fock, mol["s1e"])
+        occ = get_occ(mo_energy.detach(), nelecs)
+        mol["rdm1"] = (1 - mixing_factor) * mol["rdm1"] + mixing_factor * make_rdm1(mo_coeff, occ)
+        e, fock = predict(mol)
+    return e, mol
 
 
 # --------------------------------------------------------------------------------------------

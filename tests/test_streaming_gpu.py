@@ -92,6 +92,50 @@ def test_pointwise_forward_and_vjp(cuda_device, name, zero_frac):
             assert bool((err <= 1e-9 * rg[fin].abs() + 1e-12 * sc).all())
 
 
+@pytest.mark.parametrize("name", list(ORACLE_PW))
+def test_pointwise_second_order(cuda_device, name):
+    """VJP of the VJP (gdft_pointwise_bwd2) against torch-CPU double backward through the oracle formulas: the
+    cotangents of (inputs, out_bar) for random cotangents U of the first-order result.  This is what differentiating
+    V_xc once more -- training through the SCF loop, grad_dft/evaluate.py:917-1038 under jax.grad -- needs."""
+    N = 2053
+    rho, grho, tau, lapl = grid_quantities(N, 1993, 0.0)
+    for t in (rho, grho, tau, lapl):  # regular rows only: second derivatives do not exist at exactly-zero / fully polarised points
+        t[:4] = t[4:8]
+    ng, nt, nl = NEEDS[name]
+    dev = cuda_device
+
+    def run(device, pw):
+        leaves = [rho.to(device).requires_grad_(True), grho.to(device).requires_grad_(True) if ng else None,
+                  tau.to(device).requires_grad_(True) if nt else None, lapl.to(device).requires_grad_(True) if nl else None]
+        out = pw(*leaves)
+        g2 = torch.Generator().manual_seed(11)
+        cot = torch.randn(out.shape, generator=g2, dtype=F64).to(device).requires_grad_(True)
+        used = [x for x in leaves if x is not None]
+        first = torch.autograd.grad((out * cot).sum(), used, create_graph=True)
+        s = 0.0
+        for f in first:
+            s = s + (f * torch.randn(f.shape, generator=g2, dtype=F64).to(device)).sum()
+        second = torch.autograd.grad(s, used + [cot], allow_unused=True)
+        return [None if t is None else t.detach().cpu() for t in second], first
+
+    ref, _ = run("cpu", lambda r, g, t, l: ORACLE_PW[name](r, g if g is not None else grho, t if t is not None else tau, l if l is not None else lapl))
+    got, first = run(dev, lambda r, g, t, l: ops.pointwise(name, r, g, t, l))
+    for a, b in zip(got, ref):
+        b = torch.zeros_like(a) if b is None else b
+        a = torch.zeros_like(b) if a is None else a
+        fin = torch.isfinite(b)
+        assert bool(torch.isfinite(a[fin]).all())
+        sc = b[fin].abs().max() + 1e-300
+        assert bool(((a[fin] - b[fin]).abs() <= 1e-7 * b[fin].abs() + 1e-11 * sc).all()), name
+    # third order is not bound and must fail loudly
+    with pytest.raises(RuntimeError):
+        r3 = rho.to(dev).requires_grad_(True)
+        o = ops.pointwise("LSDA_X", r3)
+        (g1,) = torch.autograd.grad(o.sum(), r3, create_graph=True)
+        (g2_,) = torch.autograd.grad(g1.sum(), r3, create_graph=True)
+        torch.autograd.grad(g2_.sum(), r3)
+
+
 @pytest.mark.parametrize("n", [5, 12, 43, 64, 97])
 def test_eri_sweep(cuda_device, n):
     mol = synthetic_molecule(64, n, seed=1993, with_eri=True)
