@@ -10,10 +10,10 @@ from .molecule import (  # noqa: F401
 )
 from .functional import (  # noqa: F401
     DM21, Functional, NeuralFunctional, canonicalize_inputs, dm21_coefficient_inputs, dm21_combine_cinputs, dm21_combine_densities,
-    dm21_densities, dm21_hfgrads_cinputs, dm21_hfgrads_densities, stop_gradient,
+    dm21_densities, dm21_hfgrads_cinputs, dm21_hfgrads_densities, densities, stop_gradient,
 )
 from .popular_functionals import B3LYP, B88, LSDA, LYP, PW92, VWN  # noqa: F401
-from .train import energy_predictor, molecule_predictor, mse_energy_loss, simple_energy_loss, train_kernel, xc_energy_and_grads  # noqa: F401
+from .train import Harris_energy_predictor, energy_predictor, molecule_predictor, mse_energy_loss, simple_energy_loss, train_kernel, xc_energy_and_grads  # noqa: F401
 from .evaluate import (  # noqa: F401
     JittableDiis, non_scf_predictor, diff_scf_loop, diff_simple_scf_loop, make_jitted_scf_loop, make_simple_scf_loop, safe_eigh, safe_fock_solver,
 )

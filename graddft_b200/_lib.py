@@ -18,7 +18,7 @@ GDFT_RHO, GDFT_GRAD, GDFT_TAU, GDFT_LAPL, GDFT_HF = 1, 2, 4, 8, 16
 OP_DENSITY_FWD, OP_DENSITY_BWD, OP_HF_FOCK, OP_ERI_J, OP_XC_INTEGRATE = 1, 2, 3, 4, 5
 PW_IDS = {
     "LSDA_X": 0, "B88_X": 1, "VWN_C": 2, "LYP_C": 3, "PW92_C": 4, "B3LYP_SET": 5, "B88_SET": 6,
-    "DM21_INPUTS": 7, "DM21_LDA": 8, "DM21_GGA": 9, "DM21_MGGA": 10,
+    "DM21_INPUTS": 7, "DM21_LDA": 8, "DM21_GGA": 9, "DM21_MGGA": 10, "FEAT_LDA": 11, "FEAT_GGA": 12, "FEAT_MGGA": 13,
 }
 
 # name -> (restype, argtypes); mirrors include/gdft_b200.h one to one

@@ -18,19 +18,29 @@ __host__ __device__ inline int pointwise_ncols(int id) {
     case GDFT_PW_B88_SET: case GDFT_PW_DM21_GGA: return 2;
     case GDFT_PW_B3LYP_SET: case GDFT_PW_DM21_MGGA: return 4;
     case GDFT_PW_DM21_INPUTS: return 7;
+    case GDFT_PW_FEAT_LDA: return 4;
+    case GDFT_PW_FEAT_GGA: return 8;
+    case GDFT_PW_FEAT_MGGA: return 16;
     default: return 0;
   }
 }
 // bit 0: grad_rho, bit 1: lapl, bit 2: tau
 __host__ __device__ inline int pointwise_needs(int id) {
   switch (id) {
-    case GDFT_PW_B88_X: case GDFT_PW_B88_SET: case GDFT_PW_DM21_GGA: return 1;
+    case GDFT_PW_B88_X: case GDFT_PW_B88_SET: case GDFT_PW_DM21_GGA: case GDFT_PW_FEAT_GGA: return 1;
     case GDFT_PW_LYP_C: case GDFT_PW_B3LYP_SET: return 1 | 2;
-    case GDFT_PW_DM21_MGGA: return 1 | 4;
+    case GDFT_PW_DM21_MGGA: case GDFT_PW_FEAT_MGGA: return 1 | 4;
     case GDFT_PW_DM21_INPUTS: return 1 | 4;
     default: return 0;
   }
 }
+
+// output columns / columns that are actually evaluated (the rest are the upstream-zero correlation features)
+template <int ID> struct PwCols {
+  static constexpr int F = (ID == GDFT_PW_B88_SET || ID == GDFT_PW_DM21_GGA) ? 2 : (ID == GDFT_PW_B3LYP_SET || ID == GDFT_PW_DM21_MGGA) ? 4
+                         : ID == GDFT_PW_FEAT_LDA ? 4 : ID == GDFT_PW_FEAT_GGA ? 8 : ID == GDFT_PW_FEAT_MGGA ? 16 : 1;
+  static constexpr int FE = (ID == GDFT_PW_FEAT_LDA || ID == GDFT_PW_FEAT_GGA || ID == GDFT_PW_FEAT_MGGA) ? F / 2 : F;
+};
 
 // feats[] for every id except DM21_INPUTS; v = {ra, rb, saa, sbb, xa, xb}
 template <int ID, typename T>
@@ -60,6 +70,15 @@ __device__ __forceinline__ void eval_features(const T (&v)[6], double clip, T* f
         feats[col++] = term;
       }
   }
+  if (ID == GDFT_PW_FEAT_LDA || ID == GDFT_PW_FEAT_GGA || ID == GDFT_PW_FEAT_MGGA) {
+    const int nu = (ID == GDFT_PW_FEAT_LDA) ? 1 : 2, nw = (ID == GDFT_PW_FEAT_MGGA) ? 2 : 1;
+    int col = 0;
+    for (int i = 0; i < nu; i++)
+      for (int j = 0; j < nw; j++) {
+        feats[col++] = pw::mgga_term_spin(v[0], v[2], v[4], i, j, clip);
+        feats[col++] = pw::mgga_term_spin(v[1], v[3], v[5], i, j, clip);
+      }
+  }
 }
 
 struct PwArgs {
@@ -73,7 +92,7 @@ template <int ID>
 __global__ void __launch_bounds__(128) pointwise_fwd_kernel(const PwArgs a) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.N) return;
-  constexpr int F = (ID == GDFT_PW_B88_SET || ID == GDFT_PW_DM21_GGA) ? 2 : (ID == GDFT_PW_B3LYP_SET || ID == GDFT_PW_DM21_MGGA) ? 4 : 1;
+  constexpr int F = PwCols<ID>::F, FE = PwCols<ID>::FE;
   const int needs = pointwise_needs(ID);
   const double2 rho = reinterpret_cast<const double2*>(a.rho)[r];
   double v[6] = {rho.x, rho.y, 0, 0, 0, 0};
@@ -84,17 +103,17 @@ __global__ void __launch_bounds__(128) pointwise_fwd_kernel(const PwArgs a) {
   }
   if (needs & 2) { const double2 l = reinterpret_cast<const double2*>(a.lapl)[r]; v[4] = l.x; v[5] = l.y; }
   if (needs & 4) { const double2 l = reinterpret_cast<const double2*>(a.tau)[r]; v[4] = l.x; v[5] = l.y; }
-  double feats[F];
+  double feats[FE];
   eval_features<ID, double>(v, a.clip, feats);
 #pragma unroll
-  for (int f = 0; f < F; f++) a.out[r * F + f] = feats[f];
+  for (int f = 0; f < F; f++) a.out[r * F + f] = f < FE ? feats[f < FE ? f : 0] : 0.0;
 }
 
 template <int ID>
 __global__ void __launch_bounds__(128) pointwise_bwd_kernel(const PwArgs a) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.N) return;
-  constexpr int F = (ID == GDFT_PW_B88_SET || ID == GDFT_PW_DM21_GGA) ? 2 : (ID == GDFT_PW_B3LYP_SET || ID == GDFT_PW_DM21_MGGA) ? 4 : 1;
+  constexpr int F = PwCols<ID>::F, FE = PwCols<ID>::FE;
   const int needs = pointwise_needs(ID);
   typedef Dual<6> D6;
   const double2 rho = reinterpret_cast<const double2*>(a.rho)[r];
@@ -111,11 +130,11 @@ __global__ void __launch_bounds__(128) pointwise_bwd_kernel(const PwArgs a) {
   D6 v[6];
 #pragma unroll
   for (int q = 0; q < 6; q++) v[q] = pw::Make<D6>::variable(x[q], q);
-  D6 feats[F];
+  D6 feats[FE];
   eval_features<ID, D6>(v, a.clip, feats);
   double d[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-  for (int f = 0; f < F; f++) {
+  for (int f = 0; f < FE; f++) {
     const double ob = a.out_bar[r * F + f];
 #pragma unroll
     for (int q = 0; q < 6; q++) d[q] = fma(ob, feats[f].d[q], d[q]);
@@ -147,7 +166,7 @@ template <int ID>
 __global__ void __launch_bounds__(128) pointwise_bwd2_kernel(const Pw2Args a) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.N) return;
-  constexpr int F = (ID == GDFT_PW_B88_SET || ID == GDFT_PW_DM21_GGA) ? 2 : (ID == GDFT_PW_B3LYP_SET || ID == GDFT_PW_DM21_MGGA) ? 4 : 1;
+  constexpr int F = PwCols<ID>::F, FE = PwCols<ID>::FE;
   const int needs = pointwise_needs(ID);
   typedef Dual<1> B1;
   typedef Dual<6, B1> H;
@@ -182,11 +201,13 @@ __global__ void __launch_bounds__(128) pointwise_bwd2_kernel(const Pw2Args a) {
     B1 b; b.v = x[q]; b.d[0] = w[q];
     v[q] = pw::Make<H>::variable(b, q);
   }
-  H feats[F];
+  H feats[FE];
   eval_features<ID, H>(v, a.clip, feats);
   double d[6] = {0, 0, 0, 0, 0, 0}, h[6] = {0, 0, 0, 0, 0, 0};
+  if (a.out_bar_bar)
+    for (int f = FE; f < F; f++) a.out_bar_bar[r * F + f] = 0.0;
 #pragma unroll
-  for (int f = 0; f < F; f++) {
+  for (int f = 0; f < FE; f++) {
     const double ob = a.out_bar[r * F + f];
     if (a.out_bar_bar) a.out_bar_bar[r * F + f] = feats[f].v.d[0];
 #pragma unroll
@@ -299,6 +320,9 @@ static int dispatch_pw2(cudaStream_t st, int id, const Pw2Args& a) {
     case GDFT_PW_DM21_LDA: launch_pw2<GDFT_PW_DM21_LDA>(st, a); break;
     case GDFT_PW_DM21_GGA: launch_pw2<GDFT_PW_DM21_GGA>(st, a); break;
     case GDFT_PW_DM21_MGGA: launch_pw2<GDFT_PW_DM21_MGGA>(st, a); break;
+    case GDFT_PW_FEAT_LDA: launch_pw2<GDFT_PW_FEAT_LDA>(st, a); break;
+    case GDFT_PW_FEAT_GGA: launch_pw2<GDFT_PW_FEAT_GGA>(st, a); break;
+    case GDFT_PW_FEAT_MGGA: launch_pw2<GDFT_PW_FEAT_MGGA>(st, a); break;
     case GDFT_PW_DM21_INPUTS: dm21_inputs_bwd2_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a); break;
     default: return GDFT_BAD_ARGUMENT;
   }
@@ -326,6 +350,9 @@ static int dispatch_pw(bool bwd, cudaStream_t st, int id, const PwArgs& a) {
     case GDFT_PW_DM21_LDA: launch_pw<GDFT_PW_DM21_LDA>(bwd, st, a); break;
     case GDFT_PW_DM21_GGA: launch_pw<GDFT_PW_DM21_GGA>(bwd, st, a); break;
     case GDFT_PW_DM21_MGGA: launch_pw<GDFT_PW_DM21_MGGA>(bwd, st, a); break;
+    case GDFT_PW_FEAT_LDA: launch_pw<GDFT_PW_FEAT_LDA>(bwd, st, a); break;
+    case GDFT_PW_FEAT_GGA: launch_pw<GDFT_PW_FEAT_GGA>(bwd, st, a); break;
+    case GDFT_PW_FEAT_MGGA: launch_pw<GDFT_PW_FEAT_MGGA>(bwd, st, a); break;
     case GDFT_PW_DM21_INPUTS:
       if (bwd) dm21_inputs_bwd_kernel<<<grid, 128, 0, st>>>(a);
       else dm21_inputs_fwd_kernel<<<grid, 128, 0, st>>>(a);

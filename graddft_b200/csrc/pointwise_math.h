@@ -297,5 +297,26 @@ template <typename T> GDFT_HD T dm21_term_spin(const T& r, const T& sigma, const
   return f_exp2(expo);
 }
 
+// functional.py:1087-1135 (`densities`, the MGGA feature library): one spin channel of rho^{4/3} u^i w^j.  Same u as
+// dm21_term_spin; w is built from log2(tau) - 5/3 log2(rho) without the Thomas-Fermi constant (functional.py:1122).
+template <typename T> GDFT_HD T mgga_term_spin(const T& r, const T& sigma, const T& tau, int i, int j, double clip) {
+  const double beta = 1.0 / 1024.0;
+  const T log_rho = f_log2(f_clip_min(r, clip));
+  const bool live = val(log_rho) > log2(clip);
+  T expo = (4.0 / 3.0) * log_rho;
+  if (i > 0) {
+    const T log_g = f_log2(f_clip_min(sigma, clip)) / 2.0;
+    const T log_x = log_g - (4.0 / 3.0) * log_rho;
+    const T log_u = f_select(live, log_x - f_log2(1.0 + beta * f_exp2(log_x)) + log2(beta), cst<T>(0.0));
+    expo = expo + (double)i * log_u;
+  }
+  if (j > 0) {
+    const T log_1t = f_log2(f_clip_min(tau, clip)) - (5.0 / 3.0) * log_rho;
+    const T log_w = f_select(live, log_1t - f_log2(1.0 + beta * f_exp2(log_1t)) + log2(beta), cst<T>(0.0));
+    expo = expo + (double)j * log_w;
+  }
+  return f_exp2(expo);
+}
+
 }  // namespace pw
 }  // namespace gdft

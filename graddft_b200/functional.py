@@ -194,6 +194,20 @@ def dm21_densities(molecule: Molecule, functional_type: Optional[str] = "LDA", c
     return ops.pointwise(kind, rho, grho, tau, None, clip_cte)
 
 
+def densities(molecule: Molecule, functional_type: Optional[str] = "LDA", clip_cte: float = 1e-30, *_, **__) -> Array:
+    """grad_dft/functional.py:1048-1202: the u/w enhancement-factor feature library the article's neural functionals
+    train on.  Per-spin exchange columns rho^{4/3} u^i w^j followed by the same number of correlation columns, which
+    are identically zero upstream (jnp.round(e_PW92, -30) == 0) and are reproduced as zeros with
+    zero gradient.  As upstream, only the three string options work (functional.py:1087-1098)."""
+    if not isinstance(functional_type, str) or functional_type not in ("LDA", "DM21", "GGA", "MGGA"):
+        raise ValueError(f"Functional type {functional_type} not recognized, must be one of LDA, GGA, MGGA.")
+    kind = {"LDA": "FEAT_LDA", "DM21": "FEAT_LDA", "GGA": "FEAT_GGA", "MGGA": "FEAT_MGGA"}[functional_type]
+    rho = molecule.density()
+    grho = molecule.grad_density() if kind != "FEAT_LDA" else None
+    tau = molecule.kinetic_density() if kind == "FEAT_MGGA" else None
+    return ops.pointwise(kind, rho, grho, tau, None, clip_cte)
+
+
 def dm21_combine_cinputs(cinputs: Array, ehf: Array) -> Array:
     """grad_dft/functional.py:628-649: HF features appended by spin, [w0 a, w1 a, w0 b, w1 b]."""
     return torch.cat([cinputs, ehf[:, 0].T, ehf[:, 1].T], dim=1)

@@ -154,6 +154,20 @@ def _add_sym(fock: Array, v: Array, clip_cte: float) -> Array:
     return ops.fock_add_sym_(fock, v, clip_cte)
 
 
+def Harris_energy_predictor(functional: Functional, **kwargs) -> Callable:
+    """grad_dft/train.py:220-308: E_Harris = sum_i occ_i eps_i - E_J[P] + E_xc - <rdm1, V_xc> + E_nuc, with V_xc the
+    (un-symmetrised) derivative of E_xc w.r.t. rdm1 from the same fused forward + VJP build."""
+
+    def Harris_energy(params, molecule: Molecule, *args, **hkwargs) -> Array:
+        energy = (molecule.mo_occ * molecule.mo_energy).sum()
+        P = molecule.rdm1.sum(dim=0)
+        coulomb_e = -(P * ops.coulomb_j(P, molecule.rep_tensor)).sum() / 2.0
+        exc, xcfock, _ = xc_energy_and_grads(functional, params, molecule.rdm1, molecule, *args, **hkwargs)
+        return energy + exc - (molecule.rdm1 * xcfock).sum() + coulomb_e + molecule.nuclear_repulsion
+
+    return Harris_energy
+
+
 molecule_predictor = energy_predictor  # name used in the notebooks' prose (SURVEY.md section 0.2)
 
 

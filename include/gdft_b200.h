@@ -70,7 +70,13 @@ enum gdft_pointwise_id {
   GDFT_PW_DM21_LDA = 8,    /* 1 column   functional.py:534-626 (functional_type="LDA") */
   GDFT_PW_DM21_GGA = 9,    /* 2 columns  functional.py:534-626 ("GGA")           */
   GDFT_PW_DM21_MGGA = 10,  /* 4 columns  functional.py:534-626 ("MGGA")          */
-  GDFT_PW_COUNT = 11
+  /* `densities` (the MGGA feature library the article's neural functionals train on), functional.py:1048-1202:
+   * per-spin rho^{4/3} u^i w^j columns [(i,j) major, spin minor], followed by as many correlation columns that are
+   * identically zero upstream (jnp.round(e_PW92, -30) == 0 and the `> clip` test on it). */
+  GDFT_PW_FEAT_LDA = 11,   /* 2 + 2 columns */
+  GDFT_PW_FEAT_GGA = 12,   /* 4 + 4 columns */
+  GDFT_PW_FEAT_MGGA = 13,  /* 8 + 8 columns */
+  GDFT_PW_COUNT = 14
 };
 
 int gdft_version(void);

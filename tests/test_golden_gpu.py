@@ -81,6 +81,7 @@ def test_dm21_features(cuda_device):
     close(gd.dm21_coefficient_inputs(m), d["out_dm21_coefficient_inputs"], 1e-11)
     for t in ("LDA", "GGA", "MGGA"):
         close(gd.dm21_densities(m, functional_type=t), d[f"out_dm21_densities_{t}"], 1e-11)
+        close(gd.densities(m, functional_type=t), d[f"out_densities_{t}"], 1e-11)  # functional.py:1048-1202 (row f3)
     ehf = m.HF_energy_density(m.omegas)
     close(gd.dm21_combine_cinputs(gd.dm21_coefficient_inputs(m), ehf), d["out_dm21_combine_cinputs"], 1e-11)
     close(gd.dm21_combine_densities(gd.dm21_densities(m), ehf), d["out_dm21_combine_densities"], 1e-11)

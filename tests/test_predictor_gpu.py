@@ -217,3 +217,18 @@ def test_gradient_through_scf_loop_hybrid_matches_traced_oracle(cuda_device):
         scale = max(float(b.abs().max()) for b in g_ref)
         for a, b, k in zip(g, g_ref, params):
             assert float((a.cpu() - b).abs().max()) < 1e-6 * scale, k
+
+
+def test_harris_energy(cuda_device):
+    """grad_dft/train.py:220-308 against the same expression on the CPU oracle."""
+    mol = synthetic_molecule(2000, 10, seed=1984, mask_frac=0.0)
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    for name in ("LSDA", "B88", "LYP"):
+        D = mol["rdm1"].clone().requires_grad_(True)
+        exc = oracle.xc_energy_of_rdm1(D, mol, name)
+        (v,) = torch.autograd.grad(exc, D)
+        P = mol["rdm1"].sum(0)
+        ref = ((mol["mo_occ"] * mol["mo_energy"]).sum() - oracle.coulomb_energy(P, mol["rep_tensor"]) + exc.detach()
+               - (mol["rdm1"] * v).sum() + mol["nuclear_repulsion"])
+        e = gd.Harris_energy_predictor(FUNCS[name])(None, m)
+        assert abs(float(e) - float(ref)) < E_TOL, name

@@ -48,11 +48,14 @@ ORACLE_PW = {
     "DM21_LDA": lambda r, g, t, l: oracle.dm21_densities(r, g, t, "LDA"),
     "DM21_GGA": lambda r, g, t, l: oracle.dm21_densities(r, g, t, "GGA"),
     "DM21_MGGA": lambda r, g, t, l: oracle.dm21_densities(r, g, t, "MGGA"),
+    "FEAT_LDA": lambda r, g, t, l: oracle.mgga_feature_densities(r, g, t, "LDA"),
+    "FEAT_GGA": lambda r, g, t, l: oracle.mgga_feature_densities(r, g, t, "GGA"),
+    "FEAT_MGGA": lambda r, g, t, l: oracle.mgga_feature_densities(r, g, t, "MGGA"),
 }
 NEEDS = {  # (grad, tau, lapl)
     "LSDA_X": (0, 0, 0), "B88_X": (1, 0, 0), "VWN_C": (0, 0, 0), "LYP_C": (1, 0, 1), "PW92_C": (0, 0, 0),
     "B3LYP_SET": (1, 0, 1), "B88_SET": (1, 0, 0), "DM21_INPUTS": (1, 1, 0), "DM21_LDA": (0, 0, 0), "DM21_GGA": (1, 0, 0),
-    "DM21_MGGA": (1, 1, 0),
+    "DM21_MGGA": (1, 1, 0), "FEAT_LDA": (0, 0, 0), "FEAT_GGA": (1, 0, 0), "FEAT_MGGA": (1, 1, 0),
 }
 
 
