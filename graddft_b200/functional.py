@@ -94,15 +94,51 @@ class Functional:
             cinputs = None
         return cinputs
 
-    def xc_energy(self, params, grid: Grid, coefficient_inputs, densities: Array, clip_cte: float = 1e-30, **kwargs) -> Array:
-        """grad_dft/functional.py:219-253: e_r = sum_f c[r,f] d[r,f]; abs_clip; quadrature with clipped weights.
-        One fused kernel (gdft_xc_integrate_fwd); its VJP is gdft_xc_integrate_bwd."""
+    def _features(self, atoms, tap: bool, clip_cte: float = 1e-30, *args, **kwargs) -> Dict[str, Any]:
+        """compute_densities + compute_coefficient_inputs (functional.py:160-217) in one go, keeping the pieces.
+        With `tap` the stop_gradient'ed pieces come back as fresh leaves ("tap_d", "tap_c"): differentiating E_xc
+        w.r.t. them in the same backward pass that yields V_xc gives the cotangents arriving at the stop_gradient
+        boundary, which is what the explicit exact-exchange routes (molecule.py:545-685) ask for again later."""
+        self._prefetch(atoms)
+
+        def stopped(t):
+            t = stop_gradient(t)
+            return t.requires_grad_(True) if tap else t
+
+        ft: Dict[str, Any] = dict(grad_densities=None, tap_d=None, grad_cinputs=None, tap_c=None, cinputs=None)
+        if self.energy_densities:
+            ft["grad_densities"] = self.energy_densities(atoms, *args, **kwargs)
+        if self.nograd_densities:
+            ft["tap_d"] = stopped(self.nograd_densities(atoms, *args, **kwargs))
+        if ft["grad_densities"] is not None and ft["tap_d"] is not None:
+            raw = self.combine_densities(ft["grad_densities"], ft["tap_d"])
+        else:
+            raw = ft["grad_densities"] if ft["grad_densities"] is not None else ft["tap_d"]
+        ft["densities_raw"] = raw
+        ft["densities"] = abs_clip(raw, clip_cte)
+        if self.coefficient_inputs:
+            ft["grad_cinputs"] = self.coefficient_inputs(atoms, *args, **kwargs)
+        if self.nograd_coefficient_inputs:
+            ft["tap_c"] = stopped(self.nograd_coefficient_inputs(atoms, *args, **kwargs))
+        if ft["grad_cinputs"] is not None and ft["tap_c"] is not None:
+            ft["cinputs"] = self.combine_inputs(ft["grad_cinputs"], ft["tap_c"])
+        else:
+            ft["cinputs"] = ft["grad_cinputs"] if ft["grad_cinputs"] is not None else ft["tap_c"]
+        return ft
+
+    def coefficients_for(self, params, coefficient_inputs, densities: Array, **kwargs) -> Array:
+        """The coefficient block c[r|1, f] xc_energy contracts with the densities (functional.py:246-250)."""
         coefficients = self.apply(params, coefficient_inputs, **kwargs)
         if coefficients.dim() == 1:
             coefficients = coefficients.unsqueeze(-1) if coefficients.shape[0] == densities.shape[0] else coefficients.unsqueeze(0)
         if coefficients.shape[-1] == 1 and densities.shape[1] != 1:
             coefficients = coefficients.expand(coefficients.shape[0], densities.shape[1])  # einsum "rf,rf->r" broadcast
-        return ops.xc_integrate(coefficients.to(densities.dtype), densities, grid.weights, clip_cte)
+        return coefficients.to(densities.dtype)
+
+    def xc_energy(self, params, grid: Grid, coefficient_inputs, densities: Array, clip_cte: float = 1e-30, **kwargs) -> Array:
+        """grad_dft/functional.py:219-253: e_r = sum_f c[r,f] d[r,f]; abs_clip; quadrature with clipped weights.
+        One fused kernel (gdft_xc_integrate_fwd); its VJP is gdft_xc_integrate_bwd."""
+        return ops.xc_integrate(self.coefficients_for(params, coefficient_inputs, densities, **kwargs), densities, grid.weights, clip_cte)
 
     def energy(self, params, atoms, *args, **kwargs) -> Array:
         """grad_dft/functional.py:255-288."""

@@ -368,11 +368,28 @@ class Molecule:
 
     def HF_density_grad_2_Fock(self, functional, params, omegas, ehf, coefficient_inputs, densities_wout_hf, **kwargs) -> Array:
         basis = self.packed_basis.select_chi(self._omega_indices(omegas))
+        b = self._memo().get("xc_build")
+        if (b is not None and not torch.is_grad_enabled() and b.matches(functional, params) and ehf is b.nograd_densities
+                and coefficient_inputs is b.cinputs and densities_wout_hf is b.grad_densities):
+            # the coefficients of this very (params, coefficient_inputs) pair were evaluated by the XC build of the same
+            # predictor call: molecule.py:600-604 with them as constants (no second pass through the network)
+            ehf_leaf = ehf.detach().requires_grad_(True)
+            with torch.enable_grad():
+                e = ops.xc_integrate(b.coefficients, functional.combine_densities(densities_wout_hf, ehf_leaf), self.grid.weights, 1e-30)
+            (gr,) = torch.autograd.grad(e, ehf_leaf)
+            return ops.hf_fock(basis, gr)
         return HF_density_grad_2_Fock(self.grid, functional, params, None, self.ao, ehf, coefficient_inputs, densities_wout_hf,
                                       _basis=basis, **kwargs)
 
     def HF_coefficient_input_grad_2_Fock(self, functional, params, omegas, ehf, cinputs_wout_hf, densities, **kwargs) -> Array:
         basis = self.packed_basis.select_chi(self._omega_indices(omegas))
+        b = self._memo().get("xc_build")
+        if (b is not None and not torch.is_grad_enabled() and b.matches(functional, params) and b.g_cinputs is not None
+                and ehf is b.nograd_cinputs and cinputs_wout_hf is b.grad_cinputs and densities is b.densities_raw):
+            # molecule.py:672-676 asks for dE_xc/d e_HF through the coefficient inputs: the cotangent that reached the
+            # stop_gradient boundary in the XC build's own backward pass (same network, same inputs; the densities there
+            # are abs_clip'ed, a difference of at most 1e-30 in magnitude -- DESIGN.md section 4)
+            return ops.hf_fock(basis, b.g_cinputs)
         return HF_coefficient_input_grad_2_Fock(self.grid, functional, params, None, self.ao, ehf, cinputs_wout_hf, densities,
                                                 _basis=basis, **kwargs)
 

@@ -40,15 +40,56 @@ def xc_energy_and_grads(functional: Functional, params, rdm1: Array, atoms: Mole
         # i.e. inside a differentiable SCF loop (evaluate.py:917-1038); energy-only losses need first order only
         create_graph = torch.is_grad_enabled() and rdm1.requires_grad
     leaf = rdm1 if (create_graph and rdm1.requires_grad) else rdm1.detach().requires_grad_(True)
+    tap = (not create_graph) and bool(functional.nograd_densities or functional.nograd_coefficient_inputs)
     with torch.enable_grad():
         at = atoms.replace(rdm1=leaf)
-        densities = functional.compute_densities(at, *args, **functional_kwargs)
-        cinputs = functional.compute_coefficient_inputs(at, *args)
-        exc = functional.xc_energy(params, at.grid, cinputs, densities, **functional_kwargs)
-        (fock_xc,) = torch.autograd.grad(exc, leaf, create_graph=create_graph, retain_graph=keep_exc_graph or create_graph)
+        if tap:
+            # hybrids: the explicit exact-exchange routes (train.py:200-213) ask for dE_xc/d e_HF through the densities and
+            # through the coefficient inputs; both cotangents arrive at the stop_gradient boundary of THIS backward pass,
+            # and the coefficients they need are the ones evaluated here.  Keep them with the build (under jit XLA's CSE
+            # merges these re-evaluations; here the predictor does, see Molecule.HF_*_grad_2_Fock).
+            clip = functional_kwargs.get("clip_cte", args[0] if args else 1e-30)
+            ft = functional._features(at, True, *args, **functional_kwargs)
+            xkw = {k: v for k, v in functional_kwargs.items() if k != "clip_cte"}
+            coefficients = functional.coefficients_for(params, ft["cinputs"], ft["densities"], **xkw)
+            exc = ops.xc_integrate(coefficients, ft["densities"], at.grid.weights, clip)
+            taps = [t for t in (ft["tap_d"], ft["tap_c"]) if t is not None]
+            grads = torch.autograd.grad(exc, [leaf] + taps, retain_graph=keep_exc_graph, allow_unused=True)
+            fock_xc = grads[0]
+            gt = dict(zip([k for k in ("tap_d", "tap_c") if ft[k] is not None], grads[1:]))
+
+            def const(x):
+                return x.detach() if isinstance(x, torch.Tensor) else x
+
+            at._memo()["xc_build"] = XCBuild(
+                functional=functional, params_key=_params_key(params), clip=float(clip), coefficients=const(coefficients),
+                grad_densities=const(ft["grad_densities"]), nograd_densities=const(ft["tap_d"]), densities_raw=const(ft["densities_raw"]),
+                grad_cinputs=const(ft["grad_cinputs"]), nograd_cinputs=const(ft["tap_c"]), cinputs=const(ft["cinputs"]),
+                g_densities=gt.get("tap_d"), g_cinputs=gt.get("tap_c"))
+        else:
+            densities = functional.compute_densities(at, *args, **functional_kwargs)
+            cinputs = functional.compute_coefficient_inputs(at, *args)
+            exc = functional.xc_energy(params, at.grid, cinputs, densities, **functional_kwargs)
+            (fock_xc,) = torch.autograd.grad(exc, leaf, create_graph=create_graph, retain_graph=keep_exc_graph or create_graph)
     if not (keep_exc_graph or create_graph):
         exc = exc.detach()  # otherwise E_xc stays differentiable w.r.t. params (first order: energy losses, train.py:312-359)
     return exc, fock_xc, at
+
+
+def _params_key(params):
+    return tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in _leaves(params)) if params is not None else None
+
+
+class XCBuild:
+    """What one first-order XC build (forward + VJP) of a hybrid functional leaves on the molecule for the explicit
+    exact-exchange routes of the same predictor call: the feature tensors (as constants), the coefficients, and the
+    cotangents of E_xc at the two stop_gradient boundaries.  Valid only for the very tensors it holds (`is` checks)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def matches(self, functional, params) -> bool:
+        return self.functional is functional and self.clip == 1e-30 and self.params_key == _params_key(params)
 
 
 def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: float = 1e-30, differentiable_fock: Optional[bool] = None,
@@ -63,6 +104,17 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
         """train.py:165-213: the explicit exact-exchange Fock terms V (one per HF route of the functional); the
         features they need are cached on `at`, so nothing is recomputed.  They do not depend on the Fock matrix
         being assembled, only on (params, rdm1)."""
+        build = at._memo().get("xc_build") if not differentiable else None
+        if build is not None and build.matches(functional, params):
+            # same rdm1, same params: the features are the ones the XC build just evaluated (pure functions of them)
+            terms = []
+            with torch.no_grad():
+                if functional.densitygrads:
+                    terms.append(functional.densitygrads(functional, params, at, build.nograd_densities, build.cinputs, build.grad_densities))
+                if functional.coefficient_input_grads:
+                    terms.append(functional.coefficient_input_grads(functional, params, at, build.nograd_cinputs, build.grad_cinputs,
+                                                                    build.densities_raw))
+            return terms
         with torch.set_grad_enabled(differentiable):
             if functional.energy_densities and functional.densitygrads:
                 grad_densities = functional.energy_densities(at, *args, **kwargs)
