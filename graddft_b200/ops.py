@@ -481,6 +481,74 @@ def pointwise(name: str, rho, grad_rho=None, tau=None, lapl=None, clip: float = 
 
 
 # ---------------------------------------------------------------------------------------------------------
+# coefficient-network residual block (row f2)
+# ---------------------------------------------------------------------------------------------------------
+LN_ELU_MAX_WIDTH = 512
+
+
+class _ResidualLayerNormElu(Function):
+    @staticmethod
+    def forward(ctx, y, res, scale, bias, eps):
+        L = lib()
+        y, res, scale, bias = _c(y), _c(res), _c(scale), _c(bias)
+        N, W = int(y.shape[0]), int(y.shape[1])
+        out = torch.empty_like(y)
+        stats = torch.empty((N, 2), dtype=F64, device=y.device)
+        with _timed("gdft_ln_elu_fwd"):
+            check(L.gdft_ln_elu_fwd(stream_ptr(), N, W, ptr(y), ptr(res), ptr(scale), ptr(bias), float(eps), ptr(out), ptr(stats)),
+                  "gdft_ln_elu_fwd")
+        ctx.save_for_backward(y, res, scale, bias, stats)
+        ctx.eps = float(eps)
+        return out
+
+    @staticmethod
+    @once_differentiable  # second order goes through the composite path, chosen up front by the caller
+    def backward(ctx, out_bar):
+        y, res, scale, bias, stats = ctx.saved_tensors
+        L = lib()
+        N, W = int(y.shape[0]), int(y.shape[1])
+        need = ctx.needs_input_grad
+        zbar = torch.empty_like(y)
+        sbar = torch.empty_like(scale) if need[2] else None
+        bbar = torch.empty_like(bias) if need[3] else None
+        ws = workspace(L.gdft_workspace_bytes(_lib.OP_LN_ELU, N, W, 0, 0), y.device) if (need[2] or need[3]) else None
+        with _timed("gdft_ln_elu_bwd"):
+            check(L.gdft_ln_elu_bwd(stream_ptr(), N, W, ptr(y), ptr(res), ptr(scale), ptr(bias), ptr(stats), ptr(_c(out_bar)), ptr(zbar),
+                                    ptr(sbar), ptr(bbar), wptr(ws), ws.numel() if ws is not None else 0), "gdft_ln_elu_bwd")
+        return (zbar if need[0] else None), (zbar if need[1] else None), sbar, bbar, None
+
+
+class first_order_build:
+    """Context in which the predictor promises that nothing evaluated inside will be differentiated twice
+    (`xc_energy_and_grads` without create_graph): first-order-only fused kernels may be used."""
+
+    depth = 0
+
+    def __init__(self, active: bool = True):
+        self.active = active
+
+    def __enter__(self):
+        if self.active:
+            first_order_build.depth += 1
+
+    def __exit__(self, *exc):
+        if self.active:
+            first_order_build.depth -= 1
+        return False
+
+
+def residual_layernorm_elu_supported(y: torch.Tensor) -> bool:
+    return (first_order_build.depth > 0 and y.is_cuda and y.dtype == F64 and y.dim() == 2 and y.shape[1] % 2 == 0
+            and y.shape[1] <= LN_ELU_MAX_WIDTH)
+
+
+def residual_layernorm_elu(y: torch.Tensor, res: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """elu(LayerNorm(y + res) * scale + bias): one fused pass forward, one reverse (first order).  The caller picks the
+    host-framework composite instead when a second derivative will be taken through it."""
+    return _ResidualLayerNormElu.apply(y, res, scale, bias, eps)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # predictor glue (no autograd: these sit after value_and_grad in grad_dft/train.py:148-215)
 # ---------------------------------------------------------------------------------------------------------
 def fock_assemble(h1e, J, rdm1_bar, clip: float = 1e-30) -> torch.Tensor:

@@ -41,7 +41,7 @@ def xc_energy_and_grads(functional: Functional, params, rdm1: Array, atoms: Mole
         create_graph = torch.is_grad_enabled() and rdm1.requires_grad
     leaf = rdm1 if (create_graph and rdm1.requires_grad) else rdm1.detach().requires_grad_(True)
     tap = (not create_graph) and bool(functional.nograd_densities or functional.nograd_coefficient_inputs)
-    with torch.enable_grad():
+    with torch.enable_grad(), ops.first_order_build(not create_graph):
         at = atoms.replace(rdm1=leaf)
         if tap:
             # hybrids: the explicit exact-exchange routes (train.py:200-213) ask for dE_xc/d e_HF through the densities and

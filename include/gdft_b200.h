@@ -54,7 +54,8 @@ enum gdft_op {
   GDFT_OP_DENSITY_BWD = 2,
   GDFT_OP_HF_FOCK = 3,
   GDFT_OP_ERI_J = 4,
-  GDFT_OP_XC_INTEGRATE = 5
+  GDFT_OP_XC_INTEGRATE = 5,
+  GDFT_OP_LN_ELU = 6 /* N = rows, n = width */
 };
 
 /* closed-form per-point feature sets (grad_dft/popular_functionals.py, grad_dft/functional.py) */
@@ -181,6 +182,17 @@ int gdft_pointwise_bwd2(gdft_stream_t stream, int64_t N, int id, double clip, co
                         const double* grad_rho, const double* tau, const double* lapl, const double* out_bar,
                         const double* u_rho, const double* u_grad_rho, const double* u_tau, const double* u_lapl,
                         double* out_bar_bar, double* rho_t, double* grad_rho_t, double* tau_t, double* lapl_t);
+
+/* ---- coefficient-network residual block ----------------------------
+ * out = elu(LayerNorm(y + res) * scale + bias) over the last axis of [N, W] (W even, <= 512), the loop body of DM21's
+ * default_nn after its Dense layer (grad_dft/functional.py:809-819; flax LayerNorm: biased variance, eps inside the
+ * square root).  res may be NULL.  stats[N,2] receives (mean, 1/sqrt(var+eps)) per row for the reverse pass.
+ * bwd: z_bar[N,W] is the cotangent of z = y + res (hence of both y and res); scale_bar / bias_bar [W] may be NULL. */
+int gdft_ln_elu_fwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* res,
+                    const double* scale, const double* bias, double eps, double* out, double* stats);
+int gdft_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* res,
+                    const double* scale, const double* bias, const double* stats, const double* out_bar,
+                    double* z_bar, double* scale_bar, double* bias_bar, void* ws, size_t ws_bytes);
 
 /* ---- predictor glue ----------------------------------------------------------------------------
  * fock = aclip(1/2 (X + X^T)), X = aclip(h1e + J + Dbar)   (grad_dft/train.py:148-163) */
