@@ -81,7 +81,7 @@ def run_reference(args, wl):
         "cpu_baseline": {"value": rate, "unit": "builds/s", "cores": cores, "kind": "port", "sample": sample, "sample_s_per_step": dt},
         "e2e": {"value": rate, "unit": "builds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -157,22 +157,24 @@ SCF_SHAPES = {
     "c2": dict(N=34_000, n=43, desc="H2O/def2-TZVP-shaped: 34k grid pts x 43 AOs, B3LYP (LSDA+B88+VWN+LYP+HF), DIIS SCF"),
     # benzene / def2-TZVP-shaped (configs[2] shape), B3LYP; rep_tensor 38.9 GB
     "c3": dict(N=500_000, n=264, desc="benzene/def2-TZVP-shaped: 500k grid pts x 264 AOs, B3LYP, DIIS SCF, rep_tensor 38.9 GB"),
+    # BASELINE configs[2]: DM21 (11 -> 256 x 6 -> 3 network, two HF ranges) energy + Fock matrix, same shape
+    "c3_dm21": dict(N=500_000, n=264, desc="benzene/def2-TZVP-shaped: 500k grid pts x 264 AOs, DM21 (seeded weights) energy_predictor call"),
 }
 
 
-def _scf_shard(N, n, rank, world, dev):
+def _scf_shard(N, n, rank, world, dev, n_omega=1):
     """Rank-local shard of a synthetic B3LYP-ready molecule: grid rows seeded per rank, n x n data replicated, the
     (p,q) rows of an 8-fold-symmetric PSD rep_tensor built directly as a row block (never materialised whole)."""
     from graddft_b200 import distributed as gdist
     from graddft_b200.synthetic import synthetic_molecule
 
     lo, hi = gdist.shard_bounds(N, rank, world)
-    mol = synthetic_molecule(hi - lo, n, n_omega=1, seed=1984 + rank, device=dev, with_eri=False, mask_frac=0.0)
+    mol = synthetic_molecule(hi - lo, n, n_omega=n_omega, seed=1984 + rank, device=dev, with_eri=False, mask_frac=0.0)
     small = synthetic_molecule(8, n, seed=1984, device=dev, with_eri=False)
     for k in ("rdm1", "mo_coeff", "mo_occ", "mo_energy", "h1e", "s1e", "nuclear_repulsion"):
         mol[k] = small[k]
     mol["weights"] = mol["weights"] * ((hi - lo) / N)
-    mol["omegas"] = [0.0]
+    mol["omegas"] = [0.0, 0.4][:n_omega]
     g = torch.Generator(device=dev).manual_seed(4242)
     Q = 2 * n
     B = torch.randn(Q, n, n, generator=g, dtype=torch.float64, device=dev)
@@ -205,7 +207,22 @@ def scf_leg(shape_key, rank, world, dev, timed_ms, dgemm_tf, hbm_gbs):
 
     sh = SCF_SHAPES[shape_key]
     N, n = sh["N"], sh["n"]
-    m = _scf_shard(N, n, rank, world, dev)
+    dm21 = shape_key.endswith("_dm21")
+    m = _scf_shard(N, n, rank, world, dev, n_omega=2 if dm21 else 1)
+    functional = gd.DM21() if dm21 else gd.B3LYP
+    params = functional.generate_DM21_weights(device=dev) if dm21 else None
+    if dm21:
+        # BASELINE configs[2]: DM21 neural functional energy + gradient (one energy_predictor call = E and the Fock matrix)
+        pred = gd.energy_predictor(functional)
+        with torch.no_grad():
+            for _ in range(2):
+                e, f = pred(params, m)
+            ms_pred = min(timed_ms(lambda: pred(params, m), 3) / 3.0 for _ in range(2))
+        res = {"workload": sh["desc"], "N": N, "n": n, "predict_ms": ms_pred, "predicts_per_s": 1e3 / ms_pred,
+               "energy_finite": bool(torch.isfinite(e)) and bool(torch.isfinite(f).all())}
+        del m, e, f
+        torch.cuda.empty_cache()
+        return res
     loops = {c: gd.diff_scf_loop(gd.B3LYP, cycles=c) for c in (2, 6)}
     out = None
     for c in (2, 6):
@@ -381,7 +398,7 @@ def run_ours(args, wl):
         else:
             dgemm_tf_all = dgemm_tf
         scf = {}
-        for key in (("c2", "c3") if world == 1 else ("c3",)):
+        for key in (("c2", "c3", "c3_dm21") if world == 1 else ("c3", "c3_dm21")):
             try:
                 scf[key] = scf_leg(key, rank, world, dev, timed, dgemm_tf_all, hbm_peak())
             except Exception as exc:  # the headline XC line must survive a failure of the secondary leg
@@ -440,12 +457,28 @@ def run_ours(args, wl):
                 scf["c2"]["cpu_baseline"] = {"value": rate, "unit": "iter/s", "cores": cores_s, "kind": "port",
                                              "sample": f"full H2O-shaped molecule, oracle diff_scf_loop (torch-CPU float64), {dt * 1e3:.0f} ms/iter"}
             line["scf"] = {"metric": "jitted_scf_iter_per_s (diff_scf_loop = make_jitted_scf_loop)", "unit": "iter/s", **scf}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(text: str) -> None:
+    """The ONE JSON line goes to the process's real stdout; everything else that libraries print there (NCCL's
+    version banner, for one) has been diverted to stderr by `main`."""
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
