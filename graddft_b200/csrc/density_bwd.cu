@@ -26,7 +26,7 @@ namespace gdft {
 
 constexpr int BWD_BKR = 16;
 constexpr int BWD_MMA_WARPS = 8;
-constexpr int BWD_THREADS = 32 * (BWD_MMA_WARPS + 1);
+constexpr int BWD_THREADS = 32 * (BWD_MMA_WARPS + 4);  // two consumer warpgroups + one producer warpgroup
 constexpr int BWD_MAX_SLOTS = 5;
 constexpr int BWD_COEF_W = 16;  // coefficient rows per grid row (planar: W[coef][Npad])
 constexpr int BWD_MAX_STAGES = 6;
@@ -41,7 +41,7 @@ struct BwdTerm {
 // (a single K-split for all tiles makes the CTAs of the big tiles the stragglers of every wave).
 struct BwdParams {
   int64_t N;
-  int npad, nsub, nterms, tc, base, rem, stages, maxq;
+  int npad, nsub, nterms, tc, base, rem, stages, maxq, layout;
   int ks_class[4], cta_prefix[5];
   BwdTerm terms[4];
   double* part;  // [kmax][2][npad][npad]
@@ -198,14 +198,16 @@ density_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   __syncthreads();
 
-  if (warp == BWD_MMA_WARPS) {
-    // ---- TMA producer ---------------------------------------------------------------------------
-    if (lane == 0) {
+  if (warp >= BWD_MMA_WARPS) {
+    // ---- producer warpgroup: hands its registers to the consumers, then lane 0 of its first warp drives TMA ----------
+    // (a lone ninth warp would sit on an SM sub-partition with two consumers and cap every thread at 168 registers;
+    //  with a whole warpgroup shrunk to 40 the two consumer warpgroups grow to 232, which the 10 x 3 warp tile needs)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == BWD_MMA_WARPS && lane == 0) {
+      int term = 0, kt = 0, st = 0;
       for (int it = 0; it < total; it++) {
-        const int term = it / ktiles, kt = it - term * ktiles;
         const BwdTerm Tm = p.terms[term];
         const int r = (int)(r_begin + (int64_t)kt * BKR);
-        const int st = it % S;
         if (it >= S) mbar_wait(&empty[st], ((it / S) - 1) & 1);
         double* sA = sStage + (size_t)st * stage_elems;
         const int nload = Tm.per_spin ? 2 : Tm.nq;
@@ -213,28 +215,62 @@ density_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tma_load_3d(sA, &tmA, &full[st], a0, r, Tm.a_plane);
         for (int q = 0; q < nload; q++) tma_load_3d(sA + A_ELEMS + q * SLOT_ELEMS, &tmP, &full[st], b0, r, Tm.slot_plane0 + q);
         tma_load_3d(sA + A_ELEMS + p.maxq * SLOT_ELEMS, &tmW, &full[st], r, 0, 0);
+        if (++st == S) st = 0;
+        if (++kt == ktiles) { kt = 0; term++; }
       }
     }
     return;
   }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
 
   // ---- MMA consumers ------------------------------------------------------------------------------
-  // warp tile = mi x nj sub-tiles with mi, nj in {MT, MT-1} (balanced split); each combination runs its own
-  // fully unrolled loop, so ragged matrix sizes cost no predication in the hot loop
-  const int wm = warp & 1, wn = warp >> 1, spin = wn >> 1, nhalf = wn & 1;
-  const int mi = wm == 0 ? (na + 1) / 2 : na / 2, row_off = wm == 0 ? 0 : 8 * ((na + 1) / 2);
-  const int nj = nhalf == 0 ? (nb + 1) / 2 : nb / 2, col_off = nhalf == 0 ? 0 : 8 * ((nb + 1) / 2);
   BwdWarpCtx w;
   w.sStage = sStage; w.full = full; w.empty = empty;
-  w.stage_elems = stage_elems; w.S = S; w.ktiles = ktiles; w.maxq = p.maxq; w.spin = spin; w.lane = lane;
-  w.a_off = t * PITCH + row_off + g; w.b_off = t * PITCH + col_off + g;
-  w.a_row = a0 + row_off; w.b_col = b0 + col_off; w.g = g; w.t = t; w.split = split;
-  if (mi == MT && nj == MT) bwd_consumer<MT, MT, MT>(p, w);
-  else if (MT > 1 && mi == MT && nj == MT - 1) bwd_consumer<MT, MT, (MT > 1 ? MT - 1 : 1)>(p, w);
-  else if (MT > 1 && mi == MT - 1 && nj == MT) bwd_consumer<MT, (MT > 1 ? MT - 1 : 1), MT>(p, w);
-  else if (MT > 1 && mi == MT - 1 && nj == MT - 1) bwd_consumer<MT, (MT > 1 ? MT - 1 : 1), (MT > 1 ? MT - 1 : 1)>(p, w);
-  else {
-    // empty warp tile (a 1-sub-tile dimension): keep the ring moving
+  w.stage_elems = stage_elems; w.S = S; w.ktiles = ktiles; w.maxq = p.maxq; w.lane = lane;
+  w.g = g; w.t = t; w.split = split;
+  bool ran = false;
+  if (p.layout == 1) {
+    // 1 x 8 warp grid: every warp spans the whole a-range of the tile (mi = na <= 2 MT A fragments per k-step) and a
+    // quarter of one spin's b-range (nj <= ceil(MT/2) B fragments), so each B fragment -- the expensive one: NQ plane
+    // loads and NQ-1 DFMAs on the pipe the DMMAs use -- is formed exactly once per CTA and feeds up to 2 MT DMMAs.
+    // The nb sub-tiles are split into four parts in descending size order; spin 1 takes the parts in reverse, so the two
+    // warps that share an SM sub-partition (warp, warp + 4) carry ceil(nb/2) sub-tiles between them.
+    constexpr int NJM = (MT + 1) / 2;
+    const int spin = warp >> 2, q = warp & 3;
+    const int pb = nb >> 2, pr = nb & 3;
+    const int qq = spin == 0 ? q : 3 - q;
+    const int nj = pb + (qq < pr ? 1 : 0);
+    const int start_desc = qq * pb + min(qq, pr);
+    const int col_off = 8 * (spin == 0 ? start_desc : nb - start_desc - nj);
+    w.spin = spin;
+    w.a_off = t * PITCH + g; w.b_off = t * PITCH + col_off + g;
+    w.a_row = a0; w.b_col = b0 + col_off;
+    const int mi = na;
+    if (nj == NJM) {
+      if (mi == 2 * MT) { bwd_consumer<MT, 2 * MT, NJM>(p, w); ran = true; }
+      else if (mi == 2 * MT - 1) { bwd_consumer<MT, 2 * MT - 1, NJM>(p, w); ran = true; }
+      else if (MT > 1 && mi == 2 * MT - 2) { bwd_consumer<MT, (MT > 1 ? 2 * MT - 2 : 1), NJM>(p, w); ran = true; }
+    } else if (NJM > 1 && nj == NJM - 1) {
+      if (mi == 2 * MT) { bwd_consumer<MT, 2 * MT, (NJM > 1 ? NJM - 1 : 1)>(p, w); ran = true; }
+      else if (mi == 2 * MT - 1) { bwd_consumer<MT, 2 * MT - 1, (NJM > 1 ? NJM - 1 : 1)>(p, w); ran = true; }
+      else if (MT > 1 && mi == 2 * MT - 2) { bwd_consumer<MT, (MT > 1 ? 2 * MT - 2 : 1), (NJM > 1 ? NJM - 1 : 1)>(p, w); ran = true; }
+    }
+  } else {
+    // 2 x 4 warp grid: warp tile = mi x nj sub-tiles with mi, nj in {MT, MT-1} (balanced split); each combination runs
+    // its own fully unrolled loop, so ragged matrix sizes cost no predication in the hot loop
+    const int wm = warp & 1, wn = warp >> 1, spin = wn >> 1, nhalf = wn & 1;
+    const int mi = wm == 0 ? (na + 1) / 2 : na / 2, row_off = wm == 0 ? 0 : 8 * ((na + 1) / 2);
+    const int nj = nhalf == 0 ? (nb + 1) / 2 : nb / 2, col_off = nhalf == 0 ? 0 : 8 * ((nb + 1) / 2);
+    w.spin = spin;
+    w.a_off = t * PITCH + row_off + g; w.b_off = t * PITCH + col_off + g;
+    w.a_row = a0 + row_off; w.b_col = b0 + col_off;
+    if (mi == MT && nj == MT) { bwd_consumer<MT, MT, MT>(p, w); ran = true; }
+    else if (MT > 1 && mi == MT && nj == MT - 1) { bwd_consumer<MT, MT, (MT > 1 ? MT - 1 : 1)>(p, w); ran = true; }
+    else if (MT > 1 && mi == MT - 1 && nj == MT) { bwd_consumer<MT, (MT > 1 ? MT - 1 : 1), MT>(p, w); ran = true; }
+    else if (MT > 1 && mi == MT - 1 && nj == MT - 1) { bwd_consumer<MT, (MT > 1 ? MT - 1 : 1), (MT > 1 ? MT - 1 : 1)>(p, w); ran = true; }
+  }
+  if (!ran) {
+    // empty warp tile (fewer sub-tiles than warps along a dimension): keep the ring moving
     for (int it = 0; it < total; it++) {
       const int st = it % S;
       mbar_wait(&full[st], (it / S) & 1);
@@ -293,7 +329,7 @@ __global__ void hf_coef_kernel(int64_t N, int64_t Npad, const double* __restrict
 }
 
 struct BwdPlan {
-  int mt, tc, base, rem, kmax, stages, ctas;
+  int mt, tc, base, rem, kmax, stages, ctas, layout;
   int ks_class[4], cta_prefix[5];
   size_t smem;
 };
@@ -334,7 +370,11 @@ static BwdPlan plan_bwd(int64_t N, int npad, int maxq) {
   const int nbig = pl.rem, nsmall = best_tc - pl.rem;
   const int count[4] = {nbig * nbig, nbig * nsmall, nsmall * nbig, nsmall * nsmall};
   const int hb = (pl.base + 2) / 2, hs = (pl.base + 1) / 2;  // ceil(size/2) of a big / small tile
-  const double work[4] = {hb * hb + 1.0, hb * hs + 1.0, hs * hb + 1.0, hs * hs + 1.0};
+  pl.layout = 1;
+  if (const char* e = getenv("GDFT_BWD_LAYOUT")) pl.layout = atoi(e) == 0 ? 0 : 1;
+  // DMMAs per k-step on the busiest SM sub-partition: 2 x 4 grid -> 2 * ceil(sa/2) * ceil(sb/2); 1 x 8 grid -> sa * ceil(sb/2)
+  const double fa_b = pl.layout ? 0.5 * (pl.base + 1) : hb, fa_s = pl.layout ? 0.5 * pl.base : hs;
+  const double work[4] = {fa_b * hb + 1.0, fa_b * hs + 1.0, fa_s * hb + 1.0, fa_s * hs + 1.0};
   double total_work = 0.0;
   int ntiles = 0;
   for (int c = 0; c < 4; c++) { total_work += count[c] * work[c]; ntiles += count[c]; }
@@ -420,7 +460,7 @@ static int run_bwd(cudaStream_t stream, int64_t N, int n, int nplanes_a, const d
     return rc;
   BwdParams p{};
   p.N = N; p.npad = npad; p.nsub = npad / 8; p.nterms = nterms; p.tc = pl.tc; p.base = pl.base; p.rem = pl.rem; p.stages = pl.stages;
-  p.maxq = maxq;
+  p.maxq = maxq; p.layout = pl.layout;
   for (int c = 0; c < 4; c++) p.ks_class[c] = pl.ks_class[c];
   for (int c = 0; c < 5; c++) p.cta_prefix[c] = pl.cta_prefix[c];
   for (int i = 0; i < nterms; i++) p.terms[i] = terms[i];
