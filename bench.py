@@ -262,6 +262,50 @@ def scf_leg(shape_key, rank, world, dev, timed_ms, dgemm_tf, hbm_gbs):
     return res
 
 
+def train_leg(rank, world, dev, timed_ms):
+    """BASELINE configs[4]: one training step (non-SCF energy loss, grad_dft/train.py:312-359,480-535) of the DM21-shaped
+    neural functional on a batch of 64 small synthetic molecules (n_i = 12 + floor(88 U), N_i = 1e4 (1 + 3 U), seed
+    1993), molecules sharded over the ranks (balanced by N n^2), one gradient all-reduce per step, Adam update."""
+    import graddft_b200 as gd
+    from graddft_b200 import distributed as gdist
+    from graddft_b200.synthetic import synthetic_molecule
+
+    g = torch.Generator().manual_seed(1993)
+    shapes = [(int(1e4 * (1 + 3 * float(torch.rand((), generator=g)))), 12 + int(88 * float(torch.rand((), generator=g)))) for _ in range(64)]
+    mine = gdist.shard_molecules([N * n * n for N, n in shapes], rank, world)
+    mols = {i: gd.molecule_from_tensors(synthetic_molecule(shapes[i][0], shapes[i][1], n_omega=2, seed=1993 + i, device=dev, mask_frac=0.0), dev)
+            for i in mine}
+    for m in mols.values():
+        m.packed_basis
+    fun = gd.DM21()
+    params = {k: v.requires_grad_(True) for k, v in fun.generate_DM21_weights(device=dev).items()}
+    leaves = list(params.values())
+    opt = torch.optim.Adam(leaves, lr=1e-4)
+    predictor = gd.non_scf_predictor(fun)
+    truths = {i: torch.tensor(-1.0 - 0.01 * i, dtype=torch.float64, device=dev) for i in mine}
+
+    def step():
+        total = torch.zeros((), dtype=torch.float64, device=dev)
+        for i in mine:  # the reference loops serially over the batch too (train.py:519)
+            out = predictor(params, mols[i])
+            total = total + ((out.energy - truths[i]) / mols[i].mo_occ.sum()) ** 2
+        loss = total / 64
+        grads = torch.autograd.grad(loss, leaves)
+        grads, loss = gdist.allreduce_gradients(list(grads), loss.detach())
+        for p_, g_ in zip(leaves, grads):
+            p_.grad = g_
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for _ in range(2):
+        loss = step()
+    ms = min(timed_ms(step, 1) for _ in range(3))
+    return {"workload": "64 synthetic molecules (n 12..100, N 1e4..4e4), DM21-shaped functional (11 -> 256 x 6 -> 3), non-SCF "
+                        "energy loss + Adam step; molecules sharded over ranks, one gradient all-reduce per step",
+            "ms_per_step": ms, "molecules_per_s": 64e3 / ms, "molecules_on_rank0": len(mine), "loss_finite": bool(torch.isfinite(loss))}
+
+
 def cpu_scf_iter_rate(N, n):
     """Oracle SCF iteration (B3LYP) on the host cores: slope between 1- and 3-cycle loops."""
     import oracle
@@ -403,6 +447,10 @@ def run_ours(args, wl):
                 scf[key] = scf_leg(key, rank, world, dev, timed, dgemm_tf_all, hbm_peak())
             except Exception as exc:  # the headline XC line must survive a failure of the secondary leg
                 scf[key] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            scf["c5_training"] = train_leg(rank, world, dev, timed)
+        except Exception as exc:
+            scf["c5_training"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # sanity: the result that went to the host is finite
     assert bool(torch.isfinite(out_host).all()), "non-finite XC build"
