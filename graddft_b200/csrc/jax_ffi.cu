@@ -112,3 +112,46 @@ extern "C" void gdft_pointwise_bwd_xla(gdft_stream_t s, void** b, const char* op
                               (d.flags & 2) ? (double*)b[8] : nullptr);
   finish(rc, (cudaStream_t)s, b[5]);
 }
+// operands: rho, grad_rho, tau, lapl, out_bar, u_rho, u_grad_rho, u_tau, u_lapl | results: out_bar_bar, rho_t, grad_rho_t, tau_t, lapl_t
+// (flags: bit 0 grad_rho, bit 1 lapl, bit 2 tau are present -- operands and results of absent quantities are 1-element dummies)
+extern "C" void gdft_pointwise_bwd2_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  const bool g = d.flags & 1, l = d.flags & 2, t = d.flags & 4;
+  int rc = gdft_pointwise_bwd2(s, d.N, d.id, d.clip, (const double*)b[0], g ? (const double*)b[1] : nullptr, t ? (const double*)b[2] : nullptr,
+                               l ? (const double*)b[3] : nullptr, (const double*)b[4], (const double*)b[5], g ? (const double*)b[6] : nullptr,
+                               t ? (const double*)b[7] : nullptr, l ? (const double*)b[8] : nullptr, (double*)b[9], (double*)b[10],
+                               g ? (double*)b[11] : nullptr, t ? (double*)b[12] : nullptr, l ? (double*)b[13] : nullptr);
+  finish(rc, (cudaStream_t)s, b[9]);
+}
+// operands: eri_rows [rows, n, n] (rows passed as N), P | results: J_rows
+extern "C" void gdft_eri_j_rows_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_eri_j_rows(s, d.n, d.N, (const double*)b[0], (const double*)b[1], (double*)b[2]);
+  finish(rc, (cudaStream_t)s, b[2]);
+}
+// operands: eri_rows, Jbar_rows | results: Pbar, ws
+extern "C" void gdft_eri_j_transpose_rows_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_eri_j_transpose_rows(s, d.n, d.N, (const double*)b[0], (const double*)b[1], (double*)b[2], b[3], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[2]);
+}
+// operands: y, res, scale, bias (N rows, width passed as n, eps as clip; flags bit 0: res present) | results: out, stats
+extern "C" void gdft_ln_elu_fwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_ln_elu_fwd(s, d.N, d.n, (const double*)b[0], (d.flags & 1) ? (const double*)b[1] : nullptr, (const double*)b[2],
+                           (const double*)b[3], d.clip, (double*)b[4], (double*)b[5]);
+  finish(rc, (cudaStream_t)s, b[4]);
+}
+// operands: y, res, scale, bias, stats, out_bar | results: z_bar, scale_bar, bias_bar, ws
+extern "C" void gdft_ln_elu_bwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_ln_elu_bwd(s, d.N, d.n, (const double*)b[0], (d.flags & 1) ? (const double*)b[1] : nullptr, (const double*)b[2],
+                           (const double*)b[3], (const double*)b[4], (const double*)b[5], (double*)b[6], (double*)b[7], (double*)b[8], b[9],
+                           d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[6]);
+}

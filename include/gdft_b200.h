@@ -218,6 +218,11 @@ void gdft_xc_integrate_fwd_xla(gdft_stream_t stream, void** buffers, const char*
 void gdft_xc_integrate_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_pointwise_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_pointwise_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_pointwise_bwd2_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_eri_j_rows_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_eri_j_transpose_rows_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_ln_elu_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_ln_elu_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 
 #ifdef __cplusplus
 }
