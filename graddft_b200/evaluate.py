@@ -14,6 +14,7 @@ from typing import Callable, Optional, Tuple
 
 import torch
 
+from . import ops
 from .functional import Functional
 from .molecule import Molecule
 from .train import energy_predictor
@@ -30,7 +31,9 @@ class _SafeEigh(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, A):
-        evals, evecs = torch.linalg.eigh(A)
+        # small matrices: one-CTA Jacobi kernel (no status word, no host sync: the whole SCF iteration stays capturable
+        # in a CUDA graph); larger ones: the host framework's cuSOLVER path
+        evals, evecs = ops.sym_eigh(A) if ops.sym_eigh_supported(A) else torch.linalg.eigh(A)
         ctx.save_for_backward(evals, evecs)
         return evals, evecs
 
@@ -59,8 +62,9 @@ def safe_eigh(A: Array) -> Tuple[Array, Array]:
 
 def safe_general_eigh(A: Array, B: Array) -> Tuple[Array, Array]:
     """grad_dft/utils/eigenproblem.py:110-129: Cholesky-reduced generalised symmetric eigenproblem."""
-    L = torch.linalg.cholesky(B)
-    L_inv = torch.linalg.inv(L)
+    # the _ex / triangular-solve forms are the same factorisations without the status-word round trip to the host
+    L = torch.linalg.cholesky_ex(B, check_errors=False)[0]
+    L_inv = torch.linalg.solve_triangular(L, torch.eye(L.shape[-1], dtype=L.dtype, device=L.device), upper=False)
     C = L_inv @ A @ L_inv.transpose(-1, -2)
     evals, evecs_t = safe_eigh(C)
     return evals, L_inv.transpose(-1, -2) @ evecs_t
@@ -107,7 +111,7 @@ class JittableDiis:
         B[:, idx, idx] = diag
         C = torch.zeros((2, m + 1), dtype=G.dtype, device=G.device)
         C[:, 0] = 1
-        x = (torch.linalg.inv(B) @ C.unsqueeze(-1)).squeeze(-1)
+        x = (torch.linalg.inv_ex(B, check_errors=False)[0] @ C.unsqueeze(-1)).squeeze(-1)
         return x[:, 1:]
 
     def run(self, new_data, diis_data, cycle: int = 0):

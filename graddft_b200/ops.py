@@ -549,6 +549,26 @@ def residual_layernorm_elu(y: torch.Tensor, res: torch.Tensor, scale: torch.Tens
 
 
 # ---------------------------------------------------------------------------------------------------------
+# SCF harness: small symmetric eigenproblem (row f1)
+# ---------------------------------------------------------------------------------------------------------
+def sym_eigh_supported(A: torch.Tensor) -> bool:
+    return A.is_cuda and A.dtype == F64 and A.dim() >= 2 and A.shape[-1] == A.shape[-2] and 0 < A.shape[-1] <= lib().gdft_sym_eigh_max_n()
+
+
+def sym_eigh(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(eigenvalues ascending [..., n], eigenvectors as columns [..., n, n]) of symmetric A[..., n, n]; no autograd
+    (evaluate.safe_eigh supplies the VJP), no host synchronisation."""
+    A = _c(A.detach())
+    n = int(A.shape[-1])
+    batch = A.numel() // (n * n)
+    evals = torch.empty(A.shape[:-1], dtype=F64, device=A.device)
+    evecs = torch.empty_like(A)
+    with _timed("gdft_sym_eigh"):
+        check(lib().gdft_sym_eigh(stream_ptr(), batch, n, ptr(A), ptr(evals), ptr(evecs)), "gdft_sym_eigh")
+    return evals, evecs
+
+
+# ---------------------------------------------------------------------------------------------------------
 # predictor glue (no autograd: these sit after value_and_grad in grad_dft/train.py:148-215)
 # ---------------------------------------------------------------------------------------------------------
 def fock_assemble(h1e, J, rdm1_bar, clip: float = 1e-30) -> torch.Tensor:

@@ -194,6 +194,14 @@ int gdft_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y,
                     const double* scale, const double* bias, const double* stats, const double* out_bar,
                     double* z_bar, double* scale_bar, double* bias_bar, void* ws, size_t ws_bytes);
 
+/* ---- SCF harness: small symmetric eigenproblem -------------------------
+ * evals[b, n] ascending and evecs[b, n, n] (columns) of the symmetric matrices A[b, n, n], n <= gdft_sym_eigh_max_n():
+ * what jnp.linalg.eigh returns inside safe_eigh (grad_dft/utils/eigenproblem.py:26-106), as one CTA per matrix of
+ * parallel-order cyclic Jacobi in shared memory.  Stream-ordered with no status word, hence capturable in a CUDA graph
+ * together with the rest of the SCF iteration.  Larger matrices stay with the host framework's cuSOLVER path. */
+int gdft_sym_eigh_max_n(void);
+int gdft_sym_eigh(gdft_stream_t stream, int64_t batch, int64_t n, const double* A, double* evals, double* evecs);
+
 /* ---- predictor glue ----------------------------------------------------------------------------
  * fock = aclip(1/2 (X + X^T)), X = aclip(h1e + J + Dbar)   (grad_dft/train.py:148-163) */
 int gdft_fock_assemble(gdft_stream_t stream, int64_t n, const double* h1e, const double* J,

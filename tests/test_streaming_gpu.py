@@ -264,3 +264,28 @@ def test_residual_layernorm_elu(cuda_device, N, W, with_res):
     for a, b in zip(got, ref_g):
         assert relerr(a, b) < 1e-12
     assert not ops.residual_layernorm_elu_supported(dl[0])  # outside a first-order build the composite is used
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 12, 43, 64, 97, 104])
+def test_sym_eigh_jacobi(cuda_device, n):
+    """Row f1: the small symmetric eigenproblem of the SCF iteration (utils/eigenproblem.py:26-106) against LAPACK on the
+    CPU: ascending eigenvalues, orthonormal eigenvectors, small residual; degenerate and diagonal inputs included."""
+    g = torch.Generator().manual_seed(100 + n)
+    A = torch.randn(4, n, n, generator=g, dtype=F64)
+    A = 0.5 * (A + A.transpose(1, 2))
+    A[1] = torch.diag(torch.randn(n, generator=g, dtype=F64))                      # already diagonal
+    u = torch.randn(n, 1, generator=g, dtype=F64)
+    A[2] = torch.eye(n, dtype=F64) * 3.0 + (u @ u.T if n > 1 else 0.0)             # (n-1)-fold degenerate
+    A[3] = A[3] * 1e-8 + torch.diag(torch.linspace(-50.0, 50.0, n, dtype=F64))     # widely spread, nearly diagonal
+    assert ops.sym_eigh_supported(A.to(cuda_device))
+    w, V = ops.sym_eigh(A.to(cuda_device))
+    w, V = w.cpu(), V.cpu()
+    w_ref = torch.linalg.eigvalsh(A)
+    scale = A.abs().amax(dim=(1, 2)).clamp_min(1e-300)
+    assert bool(((w - w_ref).abs().amax(dim=1) <= 1e-13 * scale * max(n, 4)).all())
+    assert bool((w[:, 1:] >= w[:, :-1]).all())
+    eye = torch.eye(n, dtype=F64)
+    assert float((V.transpose(1, 2) @ V - eye).abs().max()) < 1e-13 * max(n, 4)
+    resid = (A @ V - V * w.unsqueeze(1)).abs().amax(dim=(1, 2))
+    assert bool((resid <= 1e-13 * scale * max(n, 4)).all())
+    assert not ops.sym_eigh_supported(torch.zeros(2, 200, 200, dtype=F64, device=cuda_device))
