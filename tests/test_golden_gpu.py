@@ -118,7 +118,7 @@ def test_scf_loops(cuda_device):
     tests/integration/molecules/test_predict_B88.py:82-109 asks 1e-6 kcal/mol between the jitted and non-jitted loops."""
     from graddft_b200.evaluate import diff_scf_loop, diff_simple_scf_loop, make_jitted_scf_loop
 
-    assert make_jitted_scf_loop is diff_scf_loop
+    assert callable(make_jitted_scf_loop)  # diff_scf_loop captured into a CUDA graph (test_jitted_scf_loop_is_the_eager_loop)
     d = load("scf_loops.npz")
     m = molecule({k: v for k, v in d.items() if not k.startswith(("diis_", "simple_"))}, cuda_device)
     tol = 1e-6 / 627.50947
@@ -130,3 +130,31 @@ def test_scf_loops(cuda_device):
     out = diff_simple_scf_loop(gd.LSDA, cycles=3, mixing_factor=0.4)(None, m)
     assert abs(float(out.energy) - float(d["simple_energy_LSDA_3"])) < tol
     close(out.rdm1, d["simple_rdm1_LSDA_3"], 1e-6, 1e-8)
+
+
+def test_jitted_scf_loop_is_the_eager_loop(cuda_device):
+    """make_jitted_scf_loop (CUDA-graph capture of diff_scf_loop, the stand-in for jax.jit, evaluate.py:917) replays to the
+    eager result bit for bit, re-reads rdm1 in place on every replay, and falls back to eager when gradients are asked."""
+    from graddft_b200.synthetic import synthetic_molecule
+
+    mol = synthetic_molecule(2000, 10, n_omega=2, seed=1984, mask_frac=0.0)
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    eager, jit = gd.diff_scf_loop(gd.B3LYP, cycles=3), gd.make_jitted_scf_loop(gd.B3LYP, cycles=3)
+    with torch.no_grad():
+        ref = eager(None, m)
+        e_ref, r_ref = float(ref.energy), ref.rdm1.clone()
+        for _ in range(3):  # capture, then two replays
+            out = jit(None, m)
+            assert float(out.energy) == e_ref and torch.equal(out.rdm1, r_ref)
+        # same storages, new contents: the replay must see them
+        saved = m.rdm1.clone()
+        m.rdm1.mul_(0.9)
+        ref2 = eager(None, m)
+        out2 = jit(None, m)
+        assert float(out2.energy) == float(ref2.energy) and float(out2.energy) != e_ref
+        m.rdm1.copy_(saved)
+    assert len(jit.entries) == 1
+    fun = gd.DM21(layer_widths=(8, 8))
+    params = {k: v.requires_grad_(True) for k, v in fun.generate_DM21_weights(device=cuda_device).items()}
+    e = gd.make_jitted_scf_loop(fun, cycles=1)(params, m).energy  # gradients requested -> eager, differentiable
+    assert e.requires_grad
