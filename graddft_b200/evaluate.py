@@ -130,6 +130,7 @@ def non_scf_predictor(functional: Functional, chunk_size: int = 1024, **kwargs) 
         predicted_e, fock = compute_energy(params, atoms, *args)
         return atoms.replace(fock=fock, energy=predicted_e)
 
+    predictor.energy_only = compute_energy.energy_only  # what an energy-only loss needs (no Fock build)
     return predictor
 
 

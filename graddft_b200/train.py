@@ -196,6 +196,21 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
         fock = abs_clip(fock, clip_cte)
         return energy, fock
 
+    def energy_only(params, atoms: Molecule, *args) -> Array:
+        """The energy output alone: E_xc forward + nonXC, no VJP.  Under `jit` XLA drops the unused Fock matrix of an
+        energy-only loss as dead code (train.py:480-575 only read `.energy`); the losses here ask for this entry instead."""
+        if atoms.__dict__.get("_shard") is not None:
+            return predict(params, atoms, *args)[0]
+        with ops.first_order_build():
+            exc = functional.energy_xc_only(params, atoms, *args, **kwargs)
+        P = atoms.rdm1.sum(dim=0)
+        if atoms.rdm1.requires_grad and torch.is_grad_enabled():
+            EJ = (P * ops.coulomb_j(P, atoms.rep_tensor)).sum() / 2.0
+        else:
+            EJ = ops.coulomb_j_and_energy(P, atoms.rep_tensor)[1]
+        return exc + (atoms.nuclear_repulsion + (P * atoms.h1e).sum() + EJ)
+
+    predict.energy_only = energy_only
     return predict
 
 
@@ -238,10 +253,11 @@ def mse_energy_loss(params, compute_energy: Callable, atoms_list, truth_energies
         from .distributed import shard_molecules
         idx = shard_molecules([m.grid_size * m.ao.shape[1] ** 2 for m in atoms_list], *ranks)
     total = 0.0
+    energy_only = getattr(compute_energy, "energy_only", None)
     for i in idx:
         atoms = atoms_list[i]
-        out = compute_energy(params, atoms)
-        diff = out.energy - truth_energies[i]
+        energy = energy_only(params, atoms) if energy_only is not None else compute_energy(params, atoms).energy
+        diff = energy - truth_energies[i]
         if elec_num_norm:
             num_elec = atoms.mo_occ.sum() if atoms.atom_index is None else (torch.as_tensor(atoms.atom_index).sum() - atoms.charge)
             diff = diff / num_elec
@@ -252,10 +268,11 @@ def mse_energy_loss(params, compute_energy: Callable, atoms_list, truth_energies
 def simple_energy_loss(params, compute_energy: Callable, atoms: Molecule, truth_energy):
     """grad_dft/train.py:537-560 (value_and_grad, has_aux): ((loss, E_pred), grads w.r.t. params)."""
     leaves = [p for p in _leaves(params) if p.requires_grad]
-    out = compute_energy(params, atoms)
-    loss = (out.energy - truth_energy) ** 2
+    energy_only = getattr(compute_energy, "energy_only", None)
+    energy = energy_only(params, atoms) if energy_only is not None else compute_energy(params, atoms).energy
+    loss = (energy - truth_energy) ** 2
     grads = torch.autograd.grad(loss, leaves)
-    return (loss.detach(), out.energy.detach()), grads
+    return (loss.detach(), energy.detach()), grads
 
 
 def _leaves(params):
