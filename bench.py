@@ -330,6 +330,52 @@ def cpu_scf_iter_rate(N, n):
     return 1.0 / per_iter, cores, per_iter
 
 
+def chi_leg(rank, world, dev, timed_ms, hbm_gbs):
+    """Row f4: the chi-generation tail at the benzene shape (n = 264): `rows` grid points per GPU with their nu[r] (n x n
+    per point, 557 KB) resident in HBM, streamed once by gdft_chi_contract; roofline = 8 n^2 bytes per point against the
+    HBM peak.  `e2e` (1 GPU only): the same points with nu arriving from host memory in 1024-point chunks through the
+    double-buffered uploader of generate_chi_tensor (PCIe-bound by construction: nu is produced on the host by libcint)."""
+    import torch.distributed as dist
+    from graddft_b200 import interface, ops
+    n, rows, chunk = 264, 8192, 1024
+    g = torch.Generator(device=dev).manual_seed(1984 + rank)
+    ao = torch.randn(rows, n, generator=g, dtype=torch.float64, device=dev)
+    D = torch.randn(2, n, n, generator=g, dtype=torch.float64, device=dev)
+    nu = torch.randn(rows, n, n, generator=g, dtype=torch.float64, device=dev)  # 4.6 GB >> L2
+    coords = torch.arange(rows, dtype=torch.float64, device=dev)[:, None].expand(rows, 3)
+    chi = torch.empty((rows, 1, 2, n), dtype=torch.float64, device=dev)
+
+    def step():
+        ops.chi_contract_(chi, 0, 0, ao, D, nu)
+
+    for _ in range(3):
+        step()
+    steps = 10
+    ms = timed_ms(step, steps) / steps
+    bytes_per_launch = 8.0 * rows * n * n
+    hbm_gbs, hbm_src = hbm_gbs
+    out = {"workload": f"chi tail at the benzene shape: {rows} grid points per GPU x nu[264,264] per point (one omega), nu resident in HBM",
+           "rows_per_gpu": rows, "n": n, "ms_per_launch": ms, "points_per_s": world * rows / (ms / 1e3),
+           "roofline": {"bound": "hbm", "kernel": "chi_contract_kernel (one pass over nu)", "achieved": bytes_per_launch / ms / 1e6,
+                        "peak": hbm_gbs, "unit": "GB/s", "frac": bytes_per_launch / ms / 1e6 / hbm_gbs, "bytes_per_launch": bytes_per_launch,
+                        "peak_source": hbm_src},
+           "finite": bool(torch.isfinite(chi).all())}
+    if world == 1:
+        host_rows = 4096
+        nu_host = nu[:host_rows].cpu()
+        cidx = torch.arange(host_rows, dtype=torch.float64)[:, None].expand(host_rows, 3)
+
+        def e2e():
+            interface.generate_chi_tensor(D, ao[:host_rows], cidx, lambda c, omega: nu_host[int(c[0, 0]):int(c[0, 0]) + len(c)], [0.0], chunk)
+
+        e2e()
+        ms_e = timed_ms(e2e, 3) / 3
+        out["e2e"] = {"value": host_rows / (ms_e / 1e3), "unit": "points/s", "h2d_bytes_per_step": 8 * host_rows * n * n,
+                      "d2h_bytes_per_step": 0, "ms_per_step": ms_e, "h2d_GBps": 8e-6 * host_rows * n * n / ms_e,
+                      "note": "nu chunks of 1024 points from pageable host memory through two pinned buffers"}
+    return out
+
+
 def hbm_peak():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -458,6 +504,11 @@ def run_ours(args, wl):
             scf["c5_training"] = train_leg(rank, world, dev, timed)
         except Exception as exc:
             scf["c5_training"] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            torch.cuda.empty_cache()
+            scf["chi_tail"] = chi_leg(rank, world, dev, timed, hbm_peak())
+        except Exception as exc:
+            scf["chi_tail"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # sanity: the result that went to the host is finite
     assert bool(torch.isfinite(out_host).all()), "non-finite XC build"

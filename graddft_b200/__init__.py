@@ -17,3 +17,4 @@ from .train import Harris_energy_predictor, energy_predictor, molecule_predictor
 from .evaluate import (  # noqa: F401
     JittableDiis, non_scf_predictor, diff_scf_loop, diff_simple_scf_loop, make_jitted_scf_loop, make_simple_scf_loop, safe_eigh, safe_fock_solver,
 )
+from .interface import Archive, generate_chi_tensor, loader, make_reaction, save_molecule_data, saver  # noqa: F401,E402

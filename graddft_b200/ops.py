@@ -569,6 +569,32 @@ def sym_eigh(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 # ---------------------------------------------------------------------------------------------------------
+# chi generation tail (row f4)
+# ---------------------------------------------------------------------------------------------------------
+def chi_contract_(chi: torch.Tensor, start: int, w: int, ao: torch.Tensor, rdm1: torch.Tensor, nu: torch.Tensor) -> torch.Tensor:
+    """chi[start:start+Nc, w] = einsum("sbd,rb,rda->rsa", rdm1, ao[start:start+Nc], nu) written in place into the
+    reference-layout tensor chi[N, W, 2, n] (grad_dft/interface/pyscf.py:1110-1124); nu[Nc, n, n] is one _nu_chunk."""
+    if chi.dtype != F64 or not chi.is_contiguous() or chi.dim() != 4:
+        raise TypeError("chi must be a contiguous float64 [N, W, 2, n] tensor")
+    ao, rdm1, nu = _c(ao), _c(rdm1.detach()), _c(nu)
+    N, W, two, n = (int(x) for x in chi.shape)
+    Nc = int(nu.shape[0])
+    if two != 2 or tuple(nu.shape) != (Nc, n, n) or tuple(rdm1.shape) != (2, n, n) or tuple(ao.shape) != (N, n):
+        raise TypeError(f"shape mismatch: chi {tuple(chi.shape)}, nu {tuple(nu.shape)}, rdm1 {tuple(rdm1.shape)}, ao {tuple(ao.shape)}")
+    if not (0 <= start and start + Nc <= N and 0 <= w < W):
+        raise IndexError("chunk outside the grid / omega outside the list")
+    if Nc == 0:
+        return chi
+    ptr(chi), ptr(ao)  # device / dtype / contiguity checks
+    from ctypes import c_void_p
+    ao_p = c_void_p(ao.data_ptr() + 8 * start * n)
+    chi_p = c_void_p(chi.data_ptr() + 8 * ((start * W + w) * 2 * n))
+    with _timed("gdft_chi_contract"):
+        check(lib().gdft_chi_contract(stream_ptr(), Nc, n, ao_p, n, ptr(rdm1), ptr(nu), chi_p, W * 2 * n), "gdft_chi_contract")
+    return chi
+
+
+# ---------------------------------------------------------------------------------------------------------
 # predictor glue (no autograd: these sit after value_and_grad in grad_dft/train.py:148-215)
 # ---------------------------------------------------------------------------------------------------------
 def fock_assemble(h1e, J, rdm1_bar, clip: float = 1e-30) -> torch.Tensor:

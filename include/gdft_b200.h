@@ -202,6 +202,18 @@ int gdft_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y,
 int gdft_sym_eigh_max_n(void);
 int gdft_sym_eigh(gdft_stream_t stream, int64_t batch, int64_t n, const double* A, double* evals, double* evecs);
 
+/* ---- chi generation tail ----------------------------------------------
+ * chi[r, s, a] = sum_{b,d} rdm1[s,b,d] ao[r,b] nu[r,d,a] for the Nc grid points of one nu chunk and one
+ * range-separation parameter: the "...bd,b,da->...a" einsum that generate_chi_tensor vmaps over a chunk
+ * (grad_dft/interface/pyscf.py:1110-1119); nu[Nc,n,n] are the per-point screened-Coulomb integrals that
+ * _nu_chunk yields (grad_dft/external/_hf_density.py:69-103; libcint, out of path).  Row r of the chunk reads
+ * ao + r*ao_ld (n values) and writes chi + r*chi_ld ([2, n] contiguous), so the caller can point `chi` at
+ * chi_full[start, w, 0, 0] with chi_ld = W*2*n (the reference layout chi[N,W,2,n], grad_dft/molecule.py:92) and
+ * no concatenate/stack pass is needed.  One HBM pass over nu (8 n^2 bytes per point).  n <= gdft_chi_contract_max_n(). */
+int64_t gdft_chi_contract_max_n(void);
+int gdft_chi_contract(gdft_stream_t stream, int64_t Nc, int64_t n, const double* ao, int64_t ao_ld,
+                      const double* rdm1 /*[2,n,n]*/, const double* nu /*[Nc,n,n]*/, double* chi, int64_t chi_ld);
+
 /* ---- predictor glue ----------------------------------------------------------------------------
  * fock = aclip(1/2 (X + X^T)), X = aclip(h1e + J + Dbar)   (grad_dft/train.py:148-163) */
 int gdft_fock_assemble(gdft_stream_t stream, int64_t n, const double* h1e, const double* J,

@@ -28,7 +28,7 @@ __all__ = [
     "dm21_mlp", "dm21_mlp_init", "mgga_feature_densities",
     "xc_energy_of_rdm1", "predict_b3lyp", "predict_semilocal", "predict_dm21",
     "density_vjp_formula", "safe_fock_solver", "jittable_diis_run", "diff_scf_loop_energy",
-    "predict_dm21_traced", "diff_simple_scf_loop_energy",
+    "predict_dm21_traced", "diff_simple_scf_loop_energy", "generate_chi_tensor",
 ]
 
 
@@ -656,3 +656,26 @@ def diff_scf_loop_energy(mol: dict, predict: Callable, cycles: int, max_diis: in
         e, fock = predict(mol)
         mol["fock"] = fock
     return e, mol
+
+
+# --------------------------------------------------------------------------------------------
+# chi generation tail  (grad_dft/interface/pyscf.py)
+# --------------------------------------------------------------------------------------------
+def generate_chi_tensor(rdm1: torch.Tensor, ao: torch.Tensor, grid_coords: torch.Tensor, nu_fn: Callable, omegas: Sequence[float],
+                        chunk_size: Optional[int] = 1024) -> torch.Tensor:
+    """interface/pyscf.py:1110-1124 -- chi[r, w, s, a] = einsum("sbd,b,da->sa", rdm1, ao[r], nu_w[r]) chunk by chunk
+    (`_nu_chunk`, external/_hf_density.py:69-103, yields nu for `chunk_size` grid points at a time; nu_fn(coords, omega)
+    stands for libcint's int1e_grids), concatenated over chunks and stacked over omegas on axis 1."""
+    chi = []
+    N = ao.shape[0]
+    chunk_size = chunk_size or N
+    for omega in omegas:
+        if omega < 0:
+            raise ValueError("Range-separated parameter omega must be non-negative!")  # _hf_density.py:92-93
+        parts = []
+        for i in range(0, N, chunk_size):
+            j = min(i + chunk_size, N)
+            nu = torch.as_tensor(nu_fn(grid_coords[i:j], omega), dtype=F64)
+            parts.append(torch.einsum("sbd,rb,rda->rsa", rdm1, ao[i:j], nu))
+        chi.append(torch.cat(parts, dim=0))
+    return torch.stack(chi, dim=1) if chi else torch.zeros(0, dtype=F64)
