@@ -337,7 +337,7 @@ def chi_leg(rank, world, dev, timed_ms, hbm_gbs):
     double-buffered uploader of generate_chi_tensor (PCIe-bound by construction: nu is produced on the host by libcint)."""
     import torch.distributed as dist
     from graddft_b200 import interface, ops
-    n, rows, chunk = 264, 8192, 1024
+    n, rows, chunk = 264, 9472, 1024  # 148 SMs x 2 CTAs x 8 points x 4 groups
     g = torch.Generator(device=dev).manual_seed(1984 + rank)
     ao = torch.randn(rows, n, generator=g, dtype=torch.float64, device=dev)
     D = torch.randn(2, n, n, generator=g, dtype=torch.float64, device=dev)

@@ -59,7 +59,12 @@ def test_generate_chi_tensor_edge_cases(cuda_device):
 
 # one pass narrow / two rows in flight (NJ <= 5) / one row in flight (NJ 6..8) / two passes (n > 512) / odd n; ragged chunks
 @pytest.mark.parametrize("N,n,chunk", [(37, 2, 8), (300, 43, 128), (257, 264, 100), (130, 400, 64), (70, 520, 33), (41, 129, 16), (9, 1, 4)])
-def test_chi_contract_vs_oracle(cuda_device, N, n, chunk):
+@pytest.mark.parametrize("kernel", ["auto", "0", "1"])  # GDFT_CHI_TMA: heuristic / register-staged / TMA-fed
+def test_chi_contract_vs_oracle(cuda_device, N, n, chunk, kernel, monkeypatch):
+    if kernel == "auto":
+        monkeypatch.delenv("GDFT_CHI_TMA", raising=False)
+    else:
+        monkeypatch.setenv("GDFT_CHI_TMA", kernel)
     g = torch.Generator().manual_seed(1984 + n)
     ao = torch.randn(N, n, generator=g, dtype=F64)
     D = torch.randn(2, n, n, generator=g, dtype=F64)  # non-symmetric: pins the index placement of "...bd,b,da->...a"
