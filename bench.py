@@ -293,8 +293,9 @@ def train_leg(rank, world, dev, timed_ms):
 
     def step():
         total = torch.zeros((), dtype=torch.float64, device=dev)
-        for i in mine:  # the reference loops serially over the batch too (train.py:519)
-            energy = predictor.energy_only(params, mols[i])  # what mse_energy_loss evaluates (the loss reads .energy only)
+        # what mse_energy_loss evaluates (the loss reads .energy only): features per molecule, one network pass per group
+        energies = predictor.energy_only_batch(params, [mols[i] for i in mine])
+        for i, energy in zip(mine, energies):
             total = total + ((energy - truths[i]) / mols[i].mo_occ.sum()) ** 2
         loss = total / 64
         grads = torch.autograd.grad(loss, leaves)

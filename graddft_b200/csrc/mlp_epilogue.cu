@@ -1,5 +1,7 @@
 // Row f2: the residual block of the DM21 coefficient network, grad_dft/functional.py:809-819,
 //   z = dense(x) + x ;  n = (z - mean z) / sqrt(var z + eps) ;  o = n * scale + bias ;  out = elu(o),
+// where dense(x) = x K + k: the library GEMM delivers y = x K, the Dense bias k is added here (gdft_dense_ln_elu_*), and its
+// cotangent -- the column sum of z_bar -- comes out of the reverse pass with the LayerNorm parameter cotangents,
 // as ONE streaming pass over the [N, W] activations after the (library) FP64 GEMM, forward and reverse.  The host
 // framework would run it as ~10 elementwise/reduction kernels per block, each a full HBM round trip of a 1 GB tensor
 // at the benzene shape; here a row lives in the registers of one warp (W <= 512 doubles: 16 per lane), the two
@@ -21,7 +23,7 @@ struct LnArgs {
   int64_t N;
   int W;
   double eps;
-  const double *y, *res, *gamma, *beta, *stats_in, *dout;
+  const double *y, *ybias, *res, *gamma, *beta, *stats_in, *dout;
   double *out, *stats_out, *dz, *partial;
 };
 
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_fwd_kernel(const LnArgs a) 
       z[i] = make_double2(0.0, 0.0);
       if (c < nv) {
         z[i] = __ldcs(y2 + c);
+        if (a.ybias) { const double2 yb = reinterpret_cast<const double2*>(a.ybias)[c]; z[i].x += yb.x; z[i].y += yb.y; }
         if (r2) { const double2 r = __ldcs(r2 + c); z[i].x += r.x; z[i].y += r.y; }
         s += z[i].x + z[i].y;
       }
@@ -69,13 +72,13 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_fwd_kernel(const LnArgs a) 
 
 template <bool PARAM_GRADS>
 __global__ void __launch_bounds__(LN_THREADS) ln_elu_bwd_kernel(const LnArgs a) {
-  extern __shared__ __align__(16) double sred[];  // [LN_WARPS][2][W] when PARAM_GRADS
+  extern __shared__ __align__(16) double sred[];  // [LN_WARPS][3][W] when PARAM_GRADS
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = a.W >> 1;
   const double inv_w = 1.0 / a.W;
-  double2 pg[LN_MAXV], pb[LN_MAXV];
+  double2 pg[LN_MAXV], pb[LN_MAXV], pz[LN_MAXV];  // column sums: scale_bar, bias_bar, and z_bar (= the Dense bias cotangent)
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; i++) pg[i] = pb[i] = make_double2(0.0, 0.0);
+  for (int i = 0; i < LN_MAXV; i++) pg[i] = pb[i] = pz[i] = make_double2(0.0, 0.0);
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < a.N; row += (int64_t)gridDim.x * LN_WARPS) {
     const double2* y2 = reinterpret_cast<const double2*>(a.y + row * a.W);
     const double2* r2 = a.res ? reinterpret_cast<const double2*>(a.res + row * a.W) : nullptr;
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_bwd_kernel(const LnArgs a) 
       nrm[i] = dn[i] = make_double2(0.0, 0.0);
       if (c < nv) {
         double2 z = __ldcs(y2 + c);
+        if (a.ybias) { const double2 yb = reinterpret_cast<const double2*>(a.ybias)[c]; z.x += yb.x; z.y += yb.y; }
         if (r2) { const double2 r = __ldcs(r2 + c); z.x += r.x; z.y += r.y; }
         const double2 g = reinterpret_cast<const double2*>(a.gamma)[c], b = reinterpret_cast<const double2*>(a.beta)[c];
         const double2 dy = __ldcs(d2 + c);
@@ -109,7 +113,11 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_bwd_kernel(const LnArgs a) 
 #pragma unroll
     for (int i = 0; i < LN_MAXV; i++) {
       const int c = lane + 32 * i;
-      if (c < nv) z2[c] = make_double2(rstd * (dn[i].x - m1 - nrm[i].x * m2), rstd * (dn[i].y - m1 - nrm[i].y * m2));
+      if (c < nv) {
+        const double2 zb = make_double2(rstd * (dn[i].x - m1 - nrm[i].x * m2), rstd * (dn[i].y - m1 - nrm[i].y * m2));
+        z2[c] = zb;
+        if (PARAM_GRADS) { pz[i].x += zb.x; pz[i].y += zb.y; }
+      }
     }
   }
   if (PARAM_GRADS) {
@@ -117,33 +125,55 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_bwd_kernel(const LnArgs a) 
 #pragma unroll
     for (int i = 0; i < LN_MAXV; i++) {
       const int c = lane + 32 * i;
-      if (c < nv) { s2p[(warp * 2 + 0) * nv + c] = pg[i]; s2p[(warp * 2 + 1) * nv + c] = pb[i]; }
+      if (c < nv) { s2p[(warp * 3 + 0) * nv + c] = pg[i]; s2p[(warp * 3 + 1) * nv + c] = pb[i]; s2p[(warp * 3 + 2) * nv + c] = pz[i]; }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 2 * a.W; idx += LN_THREADS) {  // idx = which * W + col
+    for (int idx = threadIdx.x; idx < 3 * a.W; idx += LN_THREADS) {  // idx = which * W + col
       double acc = 0.0;
-      for (int w = 0; w < LN_WARPS; w++) acc += sred[(size_t)w * 2 * a.W + idx];
-      a.partial[(size_t)blockIdx.x * 2 * a.W + idx] = acc;
+      for (int w = 0; w < LN_WARPS; w++) acc += sred[(size_t)w * 3 * a.W + idx];
+      a.partial[(size_t)blockIdx.x * 3 * a.W + idx] = acc;
     }
   }
 }
 
-// out[which][col] = sum_b partial[b][which][col]  (fixed order)
-__global__ void ln_param_reduce_kernel(int nblocks, int W, const double* __restrict__ partial, double* __restrict__ dgamma,
-                                       double* __restrict__ dbeta) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * W) return;
+// out[which][col] = sum_b partial[b][which][col]  (fixed order).  32 outputs x 8 block-groups per CTA: group g sums
+// b = g, g+8, ... with four independent loads in flight, the groups are added in order through shared memory (a serial
+// loop over the ~600 partial rows is a chain of dependent L2 round trips: 34 us per call).
+constexpr int LNR_OUT = 32, LNR_G = 8;
+__global__ void __launch_bounds__(LNR_OUT* LNR_G) ln_param_reduce_kernel(int nblocks, int W, const double* __restrict__ partial,
+                                                                         double* __restrict__ dgamma, double* __restrict__ dbeta,
+                                                                         double* __restrict__ dybias) {
+  __shared__ double red[LNR_G][LNR_OUT];
+  const int o = threadIdx.x & (LNR_OUT - 1), g = threadIdx.x / LNR_OUT;
+  const int idx = blockIdx.x * LNR_OUT + o;
+  const size_t stride = (size_t)3 * W;
   double acc = 0.0;
-  for (int b = 0; b < nblocks; b++) acc += partial[(size_t)b * 2 * W + idx];
-  if (idx < W) { if (dgamma) dgamma[idx] = acc; }
-  else if (dbeta) dbeta[idx - W] = acc;
+  if (idx < 3 * W) {
+    const double* src = partial + idx;
+    int b = g;
+    for (; b + 3 * LNR_G < nblocks; b += 4 * LNR_G) {
+      const double v0 = src[(size_t)b * stride], v1 = src[(size_t)(b + LNR_G) * stride];
+      const double v2 = src[(size_t)(b + 2 * LNR_G) * stride], v3 = src[(size_t)(b + 3 * LNR_G) * stride];
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; b < nblocks; b += LNR_G) acc += src[(size_t)b * stride];
+  }
+  red[g][o] = acc;
+  __syncthreads();
+  if (g == 0 && idx < 3 * W) {
+    double t = red[0][o];
+#pragma unroll
+    for (int j = 1; j < LNR_G; j++) t += red[j][o];
+    double* dst = idx < W ? dgamma : idx < 2 * W ? dbeta : dybias;
+    if (dst) dst[idx % W] = t;
+  }
 }
 
 static int ln_grid(int64_t N) { return (int)imin64(LN_MAX_CTAS, (N + LN_WARPS - 1) / LN_WARPS); }
 
 size_t ln_elu_workspace(int64_t N, int64_t W) {
   if (N <= 0 || W <= 0) return 0;
-  return (size_t)ln_grid(N) * 2 * (size_t)W * 8 + 256;
+  return (size_t)ln_grid(N) * 3 * (size_t)W * 8 + 256;
 }
 
 static int ln_check(int64_t N, int64_t W) {
@@ -155,43 +185,57 @@ static int ln_check(int64_t N, int64_t W) {
 
 using namespace gdft;
 
-extern "C" int gdft_ln_elu_fwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* res, const double* scale,
-                               const double* bias, double eps, double* out, double* stats) {
+extern "C" int gdft_dense_ln_elu_fwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* ybias, const double* res,
+                                     const double* scale, const double* bias, double eps, double* out, double* stats) {
   if (int rc = ln_check(N, W)) return rc;
   if (!y || !scale || !bias || !out) return GDFT_BAD_ARGUMENT;
-  if (!aligned16(y) || !aligned16(res) || !aligned16(scale) || !aligned16(bias) || !aligned16(out) || !aligned16(stats)) return GDFT_BAD_ALIGNMENT;
+  if (!aligned16(y) || !aligned16(ybias) || !aligned16(res) || !aligned16(scale) || !aligned16(bias) || !aligned16(out) || !aligned16(stats))
+    return GDFT_BAD_ALIGNMENT;
   LnArgs a{};
-  a.N = N; a.W = (int)W; a.eps = eps; a.y = y; a.res = res; a.gamma = scale; a.beta = bias; a.out = out; a.stats_out = stats;
+  a.N = N; a.W = (int)W; a.eps = eps; a.y = y; a.ybias = ybias; a.res = res; a.gamma = scale; a.beta = bias; a.out = out; a.stats_out = stats;
   ln_elu_fwd_kernel<<<ln_grid(N), LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
 
-extern "C" int gdft_ln_elu_bwd(gdft_stream_t stream_, int64_t N, int64_t W, const double* y, const double* res, const double* scale,
-                               const double* bias, const double* stats, const double* out_bar, double* z_bar, double* scale_bar,
-                               double* bias_bar, void* ws, size_t ws_bytes) {
+extern "C" int gdft_ln_elu_fwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* res, const double* scale,
+                               const double* bias, double eps, double* out, double* stats) {
+  return gdft_dense_ln_elu_fwd(stream, N, W, y, nullptr, res, scale, bias, eps, out, stats);
+}
+
+extern "C" int gdft_dense_ln_elu_bwd(gdft_stream_t stream_, int64_t N, int64_t W, const double* y, const double* ybias, const double* res,
+                                     const double* scale, const double* bias, const double* stats, const double* out_bar, double* z_bar,
+                                     double* scale_bar, double* bias_bar, double* ybias_bar, void* ws, size_t ws_bytes) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = ln_check(N, W)) return rc;
   if (!y || !scale || !bias || !stats || !out_bar || !z_bar) return GDFT_BAD_ARGUMENT;
-  if (!aligned16(y) || !aligned16(res) || !aligned16(scale) || !aligned16(bias) || !aligned16(stats) || !aligned16(out_bar) ||
-      !aligned16(z_bar) || !aligned16(ws))
+  if (!aligned16(y) || !aligned16(ybias) || !aligned16(res) || !aligned16(scale) || !aligned16(bias) || !aligned16(stats) ||
+      !aligned16(out_bar) || !aligned16(z_bar) || !aligned16(ws))
     return GDFT_BAD_ALIGNMENT;
-  const bool pgrads = scale_bar || bias_bar;
+  const bool pgrads = scale_bar || bias_bar || ybias_bar;
   if (pgrads && ws_bytes < ln_elu_workspace(N, W)) return GDFT_WORKSPACE_TOO_SMALL;
   LnArgs a{};
-  a.N = N; a.W = (int)W; a.y = y; a.res = res; a.gamma = scale; a.beta = bias; a.stats_in = stats; a.dout = out_bar; a.dz = z_bar;
+  a.N = N; a.W = (int)W; a.y = y; a.ybias = ybias; a.res = res; a.gamma = scale; a.beta = bias; a.stats_in = stats; a.dout = out_bar;
+  a.dz = z_bar;
   a.partial = static_cast<double*>(ws);
   const int grid = ln_grid(N);
   if (pgrads) {
-    const size_t smem = (size_t)LN_WARPS * 2 * W * 8;
+    const size_t smem = (size_t)LN_WARPS * 3 * W * 8;
     GDFT_CUDA_TRY(cudaFuncSetAttribute(ln_elu_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ln_elu_bwd_kernel<true><<<grid, LN_THREADS, smem, stream>>>(a);
     GDFT_LAUNCH_CHECK();
-    ln_param_reduce_kernel<<<(unsigned)((2 * W + 255) / 256), 256, 0, stream>>>(grid, (int)W, a.partial, scale_bar, bias_bar);
+    ln_param_reduce_kernel<<<(unsigned)((3 * W + LNR_OUT - 1) / LNR_OUT), LNR_OUT * LNR_G, 0, stream>>>(grid, (int)W, a.partial, scale_bar,
+                                                                                                      bias_bar, ybias_bar);
     GDFT_LAUNCH_CHECK();
   } else {
     ln_elu_bwd_kernel<false><<<grid, LN_THREADS, 0, stream>>>(a);
     GDFT_LAUNCH_CHECK();
   }
   return GDFT_OK;
+}
+
+extern "C" int gdft_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* res, const double* scale,
+                               const double* bias, const double* stats, const double* out_bar, double* z_bar, double* scale_bar,
+                               double* bias_bar, void* ws, size_t ws_bytes) {
+  return gdft_dense_ln_elu_bwd(stream, N, W, y, nullptr, res, scale, bias, stats, out_bar, z_bar, scale_bar, bias_bar, nullptr, ws, ws_bytes);
 }

@@ -131,6 +131,7 @@ def non_scf_predictor(functional: Functional, chunk_size: int = 1024, **kwargs) 
         return atoms.replace(fock=fock, energy=predicted_e)
 
     predictor.energy_only = compute_energy.energy_only  # what an energy-only loss needs (no Fock build)
+    predictor.energy_only_batch = compute_energy.energy_only_batch  # ... for a batch, one network pass per group of molecules
     return predictor
 
 

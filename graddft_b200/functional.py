@@ -208,7 +208,11 @@ class NeuralFunctional(Functional):
             i = self._ln_i
             object.__setattr__(self, "_ln_i", i + 1)
             p = self._bound
-            return ops.residual_layernorm_elu(self.dense(x), x, p[f"LayerNorm_{i}.scale"], p[f"LayerNorm_{i}.bias"], eps)
+            j = self._dense_i
+            object.__setattr__(self, "_dense_i", j + 1)
+            # the Dense bias is added inside the fused pass (and its cotangent summed there): y is the bare GEMM
+            return ops.residual_layernorm_elu(x @ p[f"Dense_{j}.kernel"], x, p[f"LayerNorm_{i}.scale"], p[f"LayerNorm_{i}.bias"], eps,
+                                              ybias=p[f"Dense_{j}.bias"])
         return self.activation(self.layer_norm(self.dense(x) + x, eps))
 
     def head(self, x: Array, local_features: int, sigmoid_scale_factor: float) -> Array:

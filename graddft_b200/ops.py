@@ -487,35 +487,40 @@ LN_ELU_MAX_WIDTH = 512
 
 
 class _ResidualLayerNormElu(Function):
+    """elu(LayerNorm(y + ybias + res) * scale + bias); ybias (the Dense bias) may be None."""
+
     @staticmethod
-    def forward(ctx, y, res, scale, bias, eps):
+    def forward(ctx, y, ybias, res, scale, bias, eps):
         L = lib()
-        y, res, scale, bias = _c(y), _c(res), _c(scale), _c(bias)
+        y, ybias, res, scale, bias = _c(y), _c(ybias), _c(res), _c(scale), _c(bias)
         N, W = int(y.shape[0]), int(y.shape[1])
         out = torch.empty_like(y)
         stats = torch.empty((N, 2), dtype=F64, device=y.device)
         with _timed("gdft_ln_elu_fwd"):
-            check(L.gdft_ln_elu_fwd(stream_ptr(), N, W, ptr(y), ptr(res), ptr(scale), ptr(bias), float(eps), ptr(out), ptr(stats)),
-                  "gdft_ln_elu_fwd")
-        ctx.save_for_backward(y, res, scale, bias, stats)
+            check(L.gdft_dense_ln_elu_fwd(stream_ptr(), N, W, ptr(y), ptr(ybias), ptr(res), ptr(scale), ptr(bias), float(eps), ptr(out),
+                                          ptr(stats)), "gdft_dense_ln_elu_fwd")
+        ctx.save_for_backward(y, ybias, res, scale, bias, stats)
         ctx.eps = float(eps)
         return out
 
     @staticmethod
     @once_differentiable  # second order goes through the composite path, chosen up front by the caller
     def backward(ctx, out_bar):
-        y, res, scale, bias, stats = ctx.saved_tensors
+        y, ybias, res, scale, bias, stats = ctx.saved_tensors
         L = lib()
         N, W = int(y.shape[0]), int(y.shape[1])
         need = ctx.needs_input_grad
         zbar = torch.empty_like(y)
-        sbar = torch.empty_like(scale) if need[2] else None
-        bbar = torch.empty_like(bias) if need[3] else None
-        ws = workspace(L.gdft_workspace_bytes(_lib.OP_LN_ELU, N, W, 0, 0), y.device) if (need[2] or need[3]) else None
+        ybbar = torch.empty_like(ybias) if (ybias is not None and need[1]) else None
+        sbar = torch.empty_like(scale) if need[3] else None
+        bbar = torch.empty_like(bias) if need[4] else None
+        pg = ybbar is not None or sbar is not None or bbar is not None
+        ws = workspace(L.gdft_workspace_bytes(_lib.OP_LN_ELU, N, W, 0, 0), y.device) if pg else None
         with _timed("gdft_ln_elu_bwd"):
-            check(L.gdft_ln_elu_bwd(stream_ptr(), N, W, ptr(y), ptr(res), ptr(scale), ptr(bias), ptr(stats), ptr(_c(out_bar)), ptr(zbar),
-                                    ptr(sbar), ptr(bbar), wptr(ws), ws.numel() if ws is not None else 0), "gdft_ln_elu_bwd")
-        return (zbar if need[0] else None), (zbar if need[1] else None), sbar, bbar, None
+            check(L.gdft_dense_ln_elu_bwd(stream_ptr(), N, W, ptr(y), ptr(ybias), ptr(res), ptr(scale), ptr(bias), ptr(stats),
+                                          ptr(_c(out_bar)), ptr(zbar), ptr(sbar), ptr(bbar), ptr(ybbar), wptr(ws),
+                                          ws.numel() if ws is not None else 0), "gdft_dense_ln_elu_bwd")
+        return (zbar if need[0] else None), ybbar, (zbar if (res is not None and need[2]) else None), sbar, bbar, None
 
 
 class first_order_build:
@@ -542,10 +547,13 @@ def residual_layernorm_elu_supported(y: torch.Tensor) -> bool:
             and y.shape[1] <= LN_ELU_MAX_WIDTH)
 
 
-def residual_layernorm_elu(y: torch.Tensor, res: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
-    """elu(LayerNorm(y + res) * scale + bias): one fused pass forward, one reverse (first order).  The caller picks the
-    host-framework composite instead when a second derivative will be taken through it."""
-    return _ResidualLayerNormElu.apply(y, res, scale, bias, eps)
+def residual_layernorm_elu(y: torch.Tensor, res: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6,
+                           ybias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """elu(LayerNorm(y + ybias + res) * scale + bias): one fused pass forward, one reverse (first order).  `ybias` is the
+    bias of the Dense layer that produced y (pass the bare GEMM output as y): its broadcast add and the column-sum of
+    its cotangent ride in the same two passes.  The caller picks the host-framework composite instead when a second
+    derivative will be taken through it."""
+    return _ResidualLayerNormElu.apply(y, ybias, res, scale, bias, eps)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ merges them -- SURVEY.md Appendix B).
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -210,7 +210,44 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
             EJ = ops.coulomb_j_and_energy(P, atoms.rep_tensor)[1]
         return exc + (atoms.nuclear_repulsion + (P * atoms.h1e).sum() + EJ)
 
+    def energy_only_batch(params, atoms_list: Sequence[Molecule], *args, max_points: int = 600_000) -> List[Array]:
+        """`energy_only` for several molecules with ONE pass of the coefficient network per group of molecules (their
+        grid rows concatenated, at most `max_points` per group).  The reference evaluates a batch serially
+        (train.py:519-528); the network acts row by row, so concatenating rows changes nothing but the number of launches:
+        a training step over 64 small molecules is otherwise bound by the host's launch rate (1472 GEMM launches, the
+        host enqueueing for 240 of 267 ms).  Features, quadrature and the non-XC terms stay per molecule."""
+        atoms_list = list(atoms_list)
+        if (functional.coefficient_inputs is None and functional.nograd_coefficient_inputs is None) or any(
+                a.__dict__.get("_shard") is not None for a in atoms_list):
+            return [energy_only(params, a, *args) for a in atoms_list]
+        out: List[Optional[Array]] = [None] * len(atoms_list)
+        start = 0
+        while start < len(atoms_list):
+            end, pts = start, 0
+            while end < len(atoms_list) and (end == start or pts + atoms_list[end].grid_size <= max_points):
+                pts += atoms_list[end].grid_size
+                end += 1
+            group = atoms_list[start:end]
+            with ops.first_order_build():
+                dens = [functional.compute_densities(a, *args, **kwargs) for a in group]
+                cins = [functional.compute_coefficient_inputs(a, *args) for a in group]
+                like = torch.empty((pts, dens[0].shape[1]), dtype=dens[0].dtype, device="meta")
+                coeffs = functional.coefficients_for(params, torch.cat(cins, dim=0), like, **kwargs)
+                if coeffs.shape[0] != pts:  # row-independent coefficients: nothing to batch
+                    return [energy_only(params, a, *args) for a in atoms_list]
+                for k, (a, d, c) in enumerate(zip(group, dens, coeffs.split([a.grid_size for a in group], dim=0))):
+                    exc = ops.xc_integrate(c, d, a.grid.weights, clip_cte)
+                    P = a.rdm1.sum(dim=0)
+                    if a.rdm1.requires_grad and torch.is_grad_enabled():
+                        EJ = (P * ops.coulomb_j(P, a.rep_tensor)).sum() / 2.0
+                    else:
+                        EJ = ops.coulomb_j_and_energy(P, a.rep_tensor)[1]
+                    out[start + k] = exc + (a.nuclear_repulsion + (P * a.h1e).sum() + EJ)
+            start = end
+        return out
+
     predict.energy_only = energy_only
+    predict.energy_only_batch = energy_only_batch
     return predict
 
 
@@ -254,9 +291,15 @@ def mse_energy_loss(params, compute_energy: Callable, atoms_list, truth_energies
         idx = shard_molecules([m.grid_size * m.ao.shape[1] ** 2 for m in atoms_list], *ranks)
     total = 0.0
     energy_only = getattr(compute_energy, "energy_only", None)
+    batch = getattr(compute_energy, "energy_only_batch", None)
+    idx = list(idx)
+    batched = dict(zip(idx, batch(params, [atoms_list[i] for i in idx]))) if (batch is not None and len(idx) > 1) else {}
     for i in idx:
         atoms = atoms_list[i]
-        energy = energy_only(params, atoms) if energy_only is not None else compute_energy(params, atoms).energy
+        if i in batched:
+            energy = batched[i]
+        else:
+            energy = energy_only(params, atoms) if energy_only is not None else compute_energy(params, atoms).energy
         diff = energy - truth_energies[i]
         if elec_num_norm:
             num_elec = atoms.mo_occ.sum() if atoms.atom_index is None else (torch.as_tensor(atoms.atom_index).sum() - atoms.charge)

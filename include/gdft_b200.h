@@ -194,6 +194,17 @@ int gdft_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y,
                     const double* scale, const double* bias, const double* stats, const double* out_bar,
                     double* z_bar, double* scale_bar, double* bias_bar, void* ws, size_t ws_bytes);
 
+/* The same block with the Dense bias folded in: z = y + ybias + res where y = x K is the bare library GEMM and ybias[W]
+ * the Dense bias (flax Dense = x K + k, grad_dft/functional.py:811); the reverse pass also returns ybias_bar[W] = column
+ * sums of z_bar, so neither the broadcast add nor its reduction is a pass of its own.  ybias / ybias_bar may be NULL. */
+int gdft_dense_ln_elu_fwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* ybias,
+                          const double* res, const double* scale, const double* bias, double eps, double* out,
+                          double* stats);
+int gdft_dense_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* ybias,
+                          const double* res, const double* scale, const double* bias, const double* stats,
+                          const double* out_bar, double* z_bar, double* scale_bar, double* bias_bar,
+                          double* ybias_bar, void* ws, size_t ws_bytes);
+
 /* ---- SCF harness: small symmetric eigenproblem -------------------------
  * evals[b, n] ascending and evecs[b, n, n] (columns) of the symmetric matrices A[b, n, n], n <= gdft_sym_eigh_max_n():
  * what jnp.linalg.eigh returns inside safe_eigh (grad_dft/utils/eigenproblem.py:26-106), as one CTA per matrix of

@@ -145,6 +145,16 @@ def test_training_step_energy_loss(cuda_device):
     for a, b, k in zip(g, g_ref, params):
         assert bool(torch.isfinite(a).all())
         assert relerr(a, b) < 1e-6 or float(b.abs().max()) < 1e-13, k
+    # the batched entry (one network pass for the whole batch / per group of molecules) == the per-molecule entry
+    for max_points in (10 ** 9, 1500):
+        eb = predictor.energy_only_batch(params, ms, max_points=max_points)
+        gb = torch.autograd.grad(sum(e * (k + 1.0) for k, e in enumerate(eb)), list(params.values()))
+        es = [predictor.energy_only(params, m) for m in ms]
+        gs = torch.autograd.grad(sum(e * (k + 1.0) for k, e in enumerate(es)), list(params.values()))
+        for a, b in zip(eb, es):
+            assert abs(float(a) - float(b)) < 1e-11 * max(1.0, abs(float(b)))
+        for a, b in zip(gb, gs):
+            assert relerr(a, b.cpu()) < 1e-9 or float(b.abs().max()) < 1e-13
     opt = torch.optim.Adam(list(params.values()), lr=1e-2)
     history = []
     for _ in range(5):

@@ -235,32 +235,35 @@ def test_fock_glue(cuda_device):
     assert torch.equal(got2.cpu(), ref2)
 
 
-@pytest.mark.parametrize("N,W,with_res", [(1000, 256, True), (333, 16, True), (77, 512, False), (4097, 64, True)])
-def test_residual_layernorm_elu(cuda_device, N, W, with_res):
-    """Row f2: elu(LayerNorm(y + res) * scale + bias) (grad_dft/functional.py:809-819) fused, value and first-order
-    cotangents of (y, res, scale, bias) against the same composite in torch-CPU float64."""
+@pytest.mark.parametrize("N,W,with_res,with_ybias", [(1000, 256, True, True), (333, 16, True, False), (77, 512, False, True),
+                                                      (4097, 64, True, True), (5000, 256, True, False)])
+def test_residual_layernorm_elu(cuda_device, N, W, with_res, with_ybias):
+    """Row f2: elu(LayerNorm(y + ybias + res) * scale + bias) (grad_dft/functional.py:809-819, the Dense bias folded in) fused,
+    value and first-order cotangents of (y, ybias, res, scale, bias) against the same composite in torch-CPU float64."""
     g = torch.Generator().manual_seed(21)
     y = torch.randn(N, W, generator=g, dtype=F64) * 2.0
+    ybias = 0.5 * torch.randn(W, generator=g, dtype=F64)
     res = torch.randn(N, W, generator=g, dtype=F64)
     scale = 1.0 + 0.3 * torch.randn(W, generator=g, dtype=F64)
     bias = 0.2 * torch.randn(W, generator=g, dtype=F64)
     cot = torch.randn(N, W, generator=g, dtype=F64)
 
-    def composite(y, res, scale, bias):
-        z = y + res if with_res else y
+    def composite(y, ybias, res, scale, bias):
+        z = y + (ybias if with_ybias else 0.0) + (res if with_res else 0.0)
         mu = z.mean(dim=-1, keepdim=True)
         var = ((z - mu) ** 2).mean(dim=-1, keepdim=True)
         return torch.nn.functional.elu((z - mu) * torch.rsqrt(var + 1e-6) * scale + bias)
 
-    leaves = [t.clone().requires_grad_(True) for t in (y, res, scale, bias)]
+    use = [True, with_ybias, with_res, True, True]
+    leaves = [t.clone().requires_grad_(True) for t in (y, ybias, res, scale, bias)]
     ref = composite(*leaves)
-    ref_g = torch.autograd.grad((ref * cot).sum(), leaves if with_res else [leaves[0], leaves[2], leaves[3]])
-    dl = [t.to(cuda_device).requires_grad_(True) for t in (y, res, scale, bias)]
+    ref_g = torch.autograd.grad((ref * cot).sum(), [l for l, u in zip(leaves, use) if u])
+    dl = [t.to(cuda_device).requires_grad_(True) for t in (y, ybias, res, scale, bias)]
     with ops.first_order_build():
         assert ops.residual_layernorm_elu_supported(dl[0])
-        out = ops._ResidualLayerNormElu.apply(dl[0], dl[1] if with_res else None, dl[2], dl[3], 1e-6)
+        out = ops.residual_layernorm_elu(dl[0], dl[2] if with_res else None, dl[3], dl[4], 1e-6, ybias=dl[1] if with_ybias else None)
     assert relerr(out, ref.detach()) < 1e-13
-    got = torch.autograd.grad((out * cot.to(cuda_device)).sum(), dl if with_res else [dl[0], dl[2], dl[3]])
+    got = torch.autograd.grad((out * cot.to(cuda_device)).sum(), [l for l, u in zip(dl, use) if u])
     for a, b in zip(got, ref_g):
         assert relerr(a, b) < 1e-12
     assert not ops.residual_layernorm_elu_supported(dl[0])  # outside a first-order build the composite is used
