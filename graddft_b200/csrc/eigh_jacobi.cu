@@ -22,6 +22,15 @@
 
 namespace gdft {
 
+#ifdef GDFT_EIG_PROFILE  // tools/eigh_prof.cu: per-phase clock counters of one A thread and one V thread
+__device__ long long g_eig_prof[8];
+#define EIG_TICK(var) const long long var = clock64()
+#define EIG_ACC(slot, t0, t1, who) do { if (who) g_eig_prof[slot] += (t1) - (t0); } while (0)
+#else
+#define EIG_TICK(var)
+#define EIG_ACC(slot, t0, t1, who)
+#endif
+
 constexpr int EIG_THREADS = 512;
 constexpr int EIG_MAX_N = 104;
 constexpr int EIG_MAX_SWEEPS = 40;
@@ -201,31 +210,54 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_kernel(int n, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// n <= 64 (the H2O / H2 class): the same Brent-Luk rounds with more savings (ncu on the shared-memory version: ~200
-// instructions per warp per round on 4 warps per scheduler, 2000 clocks per round against a ~250-clock rotation chain).
-//   - warp specialisation: 8 warps carry A (the serial chain of a round), 8 warps carry V and trail by one barrier: the
-//     V update of round r overlaps the read phase and rotation chain of round r+1 (measured DFMA latency 9 clocks,
-//     rsqrt 77, sqrt 102, divide 134, CTA barrier 45: tools/fp64_latency.cu);
+// n <= 64 (the H2O / H2 class): the same Brent-Luk rounds, restructured around what the shared-memory version actually
+// spends (ncu: ~200 instructions per warp per round on 4 warps per scheduler, 2000 clocks per round; timing ablation:
+// a round's skeleton of two barriers cost 720 clocks, the V update 390, the rotation chain itself almost nothing):
+//   - ONE barrier per round.  A is kept in two copies; a round reads one and writes the rotated, permuted blocks into the
+//     other, so there is no read/write hazard, and every thread derives the rotations it needs (pair k and pair l of its
+//     block) from the diagonal blocks of the copy it reads instead of waiting for a broadcast;
+//   - warp specialisation: 8 warps carry the blocks of A, 8 warps carry V;
 //   - V never touches shared memory: row i lives in the registers of one warp, lane l holding the position pair
-//     (2l, 2l+1); the rotation is local to the lane and the position permutation of a round is two warp shuffles;
+//     (2l, 2l+1); the rotation is local to the lane, the position permutation of a round is one shuffle up and one down,
+//     and the rows of a warp are independent chains the scheduler interleaves (no per-row branches);
 //   - only the upper triangle of A is stored and updated (blocks k <= l: half the shared-memory traffic and FLOPs);
 //     a rotated element whose permuted position falls below the diagonal is stored at the transposed address;
-//   - the rotation comes from two rsqrt and no sqrt / divide: with h = d^2 + b^2, r = rsqrt(h), x = |d| r = cos 2theta
-//     and |b| r = sin 2theta:  c = sqrt((1 + x)/2) = u rsqrt(u) with u = (1 + x)/2,  |s| = sin 2theta / (2c) = |b| r rsqrt(u) / 2
-//     (no cancellation anywhere; c^2 + s^2 = u + (1 - x^2)/(4u) = 1).  The rotation is the serial part of a round.
+//   - the rotation comes from two rsqrt and no sqrt / divide (measured latencies on B200, tools/fp64_latency.cu: DFMA 9
+//     clocks, rsqrt 77, sqrt 102, divide 134, CTA barrier 45): with h = d^2 + b^2, r = rsqrt(h), x = |d| r = cos 2theta,
+//     |b| r = sin 2theta:  c = sqrt((1 + x)/2) = u rsqrt(u) with u = (1 + x)/2,  |s| = sin 2theta / (2c) = |b| r rsqrt(u) / 2
+//     (no cancellation anywhere; c^2 + s^2 = u + (1 - x^2)/(4u) = 1).
 // ---------------------------------------------------------------------------------------------------------------
-template <int NB>
+// rotation of position pair k from the current copy of A: (c, s) with c^2 + s^2 = 1 that annihilates A[2k][2k+1]
+__device__ __forceinline__ void eig_pair_rotation(const double* __restrict__ src, int m, int k, double& c, double& s) {
+  const int p = 2 * k;
+  const double2 top = *reinterpret_cast<const double2*>(src + p * m + p);  // (a_pp, a_pq)
+  const double aqq = src[(p + 1) * m + p + 1];
+  const double d = aqq - top.x, b = 2.0 * top.y;
+  const double h = fma(d, d, b * b);
+  c = 1.0; s = 0.0;
+  if (top.y != 0.0 && h > 1e-290) {
+    const double rh = rsqrt(h);
+    const double u = fma(0.5 * fabs(d), rh, 0.5);  // (1 + cos 2theta) / 2 in [1/2, 1]
+    const double ru = rsqrt(u);
+    c = u * ru;
+    s = 0.5 * fabs(b) * rh * ru;
+    if ((d < 0.0) != (b < 0.0)) s = -s;
+  }
+}
+
+template <int NB, int NR>
 __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n, const double* __restrict__ A_in, double* __restrict__ evals,
-                                                                           double* __restrict__ evecs, int dbg) {
-  // warps 0..7 own the 2 x 2 blocks of A (the latency chain of a round); warps 8..15 own V and follow one barrier behind
-  constexpr int NW = EIG_THREADS / 32, NAW = NW / 2, NVW = NW - NAW, NR = 8;  // NR: V rows per V warp (n <= 64)
+                                                                           double* __restrict__ evecs) {
+  // warps 0..7 own the 2 x 2 blocks of A, warps 8..15 own the rows of V (NR rows per warp, in registers)
+  constexpr int NW = EIG_THREADS / 32, NAW = NW / 2, NVW = NW - NAW;
   constexpr int ATHREADS = 32 * NAW;
   extern __shared__ __align__(16) double sm[];
   const int npair = (n + 1) / 2, m = 2 * npair;
-  double* sA = sm;                  // [m][m], upper triangle live
-  double* slog = sA + (size_t)m * m;  // [2][2][32]: (cos, sin) of the round, double-buffered over rounds
+  double* sA = sm;  // [2][m][m]: the round reads one copy and writes the other (upper triangles live)
   __shared__ double red[NW];
   __shared__ double s_off, s_tot;
+  __shared__ int rank[64];
+  __shared__ double slog[128];  // [2][2][32]: (cos, sin) per pair, double-buffered over rounds
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool a_warp = warp < NAW;
   const double* A = A_in + (size_t)blockIdx.x * n * n;
@@ -234,7 +266,7 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
     const int i = idx / m, j = idx - i * m;
     sA[idx] = (i < n && j < n) ? 0.5 * (A[(size_t)i * n + j] + A[(size_t)j * n + i]) : 0.0;
   }
-  // V rows in registers (V warps): row i = (warp - NAW) + NVW * q, lane l holds the position pair (2l, 2l+1)
+  // V rows: row i = (warp - NAW) + NVW * q, lane l holds the position pair (2l, 2l+1); rows >= n stay zero
   double vt[NR], vb[NR];
 #pragma unroll
   for (int q = 0; q < NR; q++) {
@@ -263,14 +295,17 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
       for (int e = 0; e < 4; e++) b_d[j][e] = rr[e] <= cc[e] ? rr[e] * m + cc[e] : cc[e] * m + rr[e];
     }
   }
+  const bool v_first = lane == 0, v_last = lane == npair - 1, single_pair = npair == 1;
+  int cur = 0;
   __syncthreads();
 
   for (int sweep = 0; sweep < EIG_MAX_SWEEPS; sweep++) {
+    const double* Ac = sA + (size_t)cur * m * m;
     double off = 0.0, tot = 0.0;
     for (int idx = tid; idx < m * m; idx += EIG_THREADS) {
       const int i = idx / m, j = idx - i * m;
       if (i <= j) {
-        const double v = sA[idx];
+        const double v = Ac[idx];
         if (i == j) tot += v * v;
         else off += 2.0 * v * v;
       }
@@ -286,88 +321,84 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
     __syncthreads();
     if (tid == 0) { double s = 0; for (int w = 0; w < NW; w++) s += red[w]; s_tot = s; }
     __syncthreads();
-    if (dbg ? sweep >= 8 : !(s_off > eig_tol(n) * s_tot)) break;  // also leaves on NaN
+    if (!(s_off > eig_tol(n) * s_tot)) break;  // also leaves on NaN
 
+    // Round r: (1) the rotation warp (warp 0, lane = pair) derives the npair rotations from the diagonal blocks of the
+    // copy of A being read and publishes them; barrier 0 (all warps); (2) the A warps write the rotated, permuted blocks
+    // into the other copy while the V warps rotate and permute their rows; barrier 1 (A warps only: the V warps run on
+    // into the next round and meet the others again at its barrier 0; the rotations are double-buffered for that).
     for (int r = 0; r < m - 1; r++) {
+      const double* src = sA + (size_t)cur * m * m;
+      double* dst = sA + (size_t)(cur ^ 1) * m * m;
       double* lc = slog + (r & 1) * 64;
       double* ls = lc + 32;
+      EIG_TICK(t_begin);
+      if (warp == 0 && lane < npair) {
+        double c, s2;
+        eig_pair_rotation(src, m, lane, c, s2);
+        lc[lane] = c;
+        ls[lane] = s2;
+      }
+      EIG_TICK(t_rot);
+      asm volatile("bar.sync 0, %0;" ::"n"(EIG_THREADS) : "memory");
+      EIG_TICK(t_bar0);
       if (a_warp) {
-        // ---- read phase; the owners of the diagonal blocks publish the rotations of this round ----
-        double2 a0[NB], a1[NB];
 #pragma unroll
         for (int j = 0; j < NB; j++) {
           if (b_k[j] >= 0) {
-            const int src = 2 * b_k[j] * m + 2 * b_l[j];
-            a0[j] = *reinterpret_cast<const double2*>(sA + src);
-            a1[j] = *reinterpret_cast<const double2*>(sA + src + m);
-            if (b_k[j] == b_l[j]) {
-              a1[j].x = a0[j].y;  // the mirror image of (p, q): the lower triangle is not maintained
-              const double apq = a0[j].y;
-              double c = 1.0, s = 0.0;
-              const double d = a1[j].y - a0[j].x, b = 2.0 * apq;
-              const double h = fma(d, d, b * b);
-              if (dbg & 2) { c = 0.8; s = 0.6; }
-              else if (apq != 0.0 && h > 1e-290) {
-                const double rh = rsqrt(h);
-                const double u = fma(0.5 * fabs(d), rh, 0.5);  // (1 + cos 2theta) / 2 in [1/2, 1]
-                const double ru = rsqrt(u);
-                c = u * ru;
-                s = 0.5 * fabs(b) * rh * ru;
-                if ((d < 0.0) != (b < 0.0)) s = -s;
-              }
-              lc[b_k[j]] = c;
-              ls[b_k[j]] = s;
-            }
+            const int k = b_k[j], l = b_l[j];
+            const int o = 2 * k * m + 2 * l;
+            const double2 a0 = *reinterpret_cast<const double2*>(src + o);
+            double2 a1 = *reinterpret_cast<const double2*>(src + o + m);
+            if (k == l) a1.x = a0.y;  // the mirror image of (p, q): the lower triangle is not maintained
+            const double ck = lc[k], sk = ls[k], cl = lc[l], sl = ls[l];
+            const double tpP = cl * a0.x - sl * a0.y, tpQ = sl * a0.x + cl * a0.y;
+            const double tqP = cl * a1.x - sl * a1.y, tqQ = sl * a1.x + cl * a1.y;
+            dst[b_d[j][0]] = ck * tpP - sk * tqP;
+            dst[b_d[j][1]] = ck * tpQ - sk * tqQ;
+            if (k != l) dst[b_d[j][2]] = sk * tpP + ck * tqP;  // diagonal block: the same slot as element 1
+            dst[b_d[j][3]] = sk * tpQ + ck * tqQ;
           }
         }
-        asm volatile("bar.sync 0, %0;" ::"n"(EIG_THREADS) : "memory");  // barrier 0, all warps: rotations visible, every block read
-        // ---- write phase: rotate (columns by pair l, then rows by pair k), store at the permuted positions ----
-#pragma unroll
-        for (int j = 0; j < NB; j++) {
-          if (b_k[j] >= 0 && !(dbg & 4)) {
-            const double ck = lc[b_k[j]], sk = ls[b_k[j]], cl = lc[b_l[j]], sl = ls[b_l[j]];
-            const double tpP = cl * a0[j].x - sl * a0[j].y, tpQ = sl * a0[j].x + cl * a0[j].y;
-            const double tqP = cl * a1[j].x - sl * a1[j].y, tqQ = sl * a1[j].x + cl * a1[j].y;
-            sA[b_d[j][0]] = ck * tpP - sk * tqP;
-            sA[b_d[j][1]] = ck * tpQ - sk * tqQ;
-            if (b_k[j] != b_l[j]) sA[b_d[j][2]] = sk * tpP + ck * tqP;  // diagonal block: the same slot as element 1
-            sA[b_d[j][3]] = sk * tpQ + ck * tqQ;
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(ATHREADS) : "memory");  // A warps only: the next round may read A
+        EIG_TICK(t_work);
+        asm volatile("bar.sync 1, %0;" ::"n"(ATHREADS) : "memory");
+        EIG_TICK(t_bar1);
+        EIG_ACC(0, t_begin, t_rot, tid == 0 && blockIdx.x == 0);   // rotation warp
+        EIG_ACC(1, t_rot, t_bar0, tid == 0 && blockIdx.x == 0);    // barrier 0
+        EIG_ACC(2, t_bar0, t_work, tid == 0 && blockIdx.x == 0);   // A update
+        EIG_ACC(3, t_work, t_bar1, tid == 0 && blockIdx.x == 0);   // barrier 1
+        EIG_ACC(4, 0, 1, tid == 0 && blockIdx.x == 0);             // rounds
       } else {
-        asm volatile("bar.sync 0, %0;" ::"n"(EIG_THREADS) : "memory");  // barrier 0 (the V warps' side of it)
         // V <- V J, then the position permutation: top'_0 = top_0, top'_1 = bot_0, top'_l = top_{l-1};
-        // bot'_l = bot_{l+1}, bot'_{npair-1} = top_{npair-1}.  Runs while the A warps are already in the next round's
-        // read phase: the rotations of round r+1 go to the other half of slog, and the A warps cannot pass barrier 0 of
-        // round r+1 (after which half r is rewritten) before this warp arrives there.
+        // bot'_l = bot_{l+1}, bot'_{npair-1} = top_{npair-1}: one shuffle up (of bot at lane 0, top elsewhere), one down
         const double cl = lane < npair ? lc[lane] : 1.0, sl = lane < npair ? ls[lane] : 0.0;
+        // straight-line over the rows (npair == 1 never permutes: v_first == v_last == lane 0 keeps t, and the value
+        // shuffled down into bot is overwritten only where it matters): the NR chains interleave in the scheduler
+        double t[NR], b[NR], up[NR], dn[NR];
+#pragma unroll
+        for (int q = 0; q < NR; q++) { t[q] = cl * vt[q] - sl * vb[q]; b[q] = sl * vt[q] + cl * vb[q]; }
+#pragma unroll
+        for (int q = 0; q < NR; q++) { up[q] = __shfl_up_sync(0xffffffffu, v_first ? b[q] : t[q], 1); dn[q] = __shfl_down_sync(0xffffffffu, b[q], 1); }
 #pragma unroll
         for (int q = 0; q < NR; q++) {
-          if ((warp - NAW) + NVW * q < n && !(dbg & 1)) {  // warp-uniform
-            const double t = cl * vt[q] - sl * vb[q], b = sl * vt[q] + cl * vb[q];
-            if (npair > 1) {
-              const double t_up = __shfl_up_sync(0xffffffffu, t, 1), b_up = __shfl_up_sync(0xffffffffu, b, 1);
-              const double b_dn = __shfl_down_sync(0xffffffffu, b, 1);
-              vt[q] = lane == 0 ? t : lane == 1 ? b_up : t_up;
-              vb[q] = lane == npair - 1 ? t : b_dn;
-            } else {
-              vt[q] = t; vb[q] = b;
-            }
-          }
+          vt[q] = v_first ? t[q] : up[q];
+          vb[q] = single_pair ? b[q] : (v_last ? t[q] : dn[q]);
         }
+        EIG_TICK(t_work);
+        EIG_ACC(5, t_bar0, t_work, tid == 32 * NAW && blockIdx.x == 0);   // V update
+        EIG_ACC(6, t_begin, t_bar0, tid == 32 * NAW && blockIdx.x == 0);  // V wait at barrier 0
       }
+      cur ^= 1;
     }
-    __syncthreads();  // sweep boundary: A complete for the convergence test
+    __syncthreads();  // sweep boundary: the V warps rejoin; A complete for the convergence test
   }
 
-  int* rank = reinterpret_cast<int*>(slog);  // 128 doubles >= 64 ints
-  __syncthreads();
+  const double* Ac = sA + (size_t)cur * m * m;
   for (int i = tid; i < n; i += EIG_THREADS) {
-    const double li = sA[i * m + i];
+    const double li = Ac[i * m + i];
     int rk = 0;
     for (int j = 0; j < n; j++) {
-      const double lj = sA[j * m + j];
+      const double lj = Ac[j * m + j];
       rk += (lj < li || (lj == li && j < i)) ? 1 : 0;
     }
     rank[i] = rk;
@@ -375,7 +406,7 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
   __syncthreads();
   double* ev = evals + (size_t)blockIdx.x * n;
   double* vec = evecs + (size_t)blockIdx.x * n * n;
-  for (int i = tid; i < n; i += EIG_THREADS) ev[rank[i]] = sA[i * m + i];
+  for (int i = tid; i < n; i += EIG_THREADS) ev[rank[i]] = Ac[i * m + i];
   if (!a_warp) {
 #pragma unroll
     for (int q = 0; q < NR; q++) {
@@ -388,14 +419,12 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
   }
 }
 
-template <int NB>
+template <int NB, int NR>
 static int launch_eig_small(cudaStream_t stream, int64_t batch, int n, const double* A, double* evals, double* evecs) {
   const int m = 2 * ((n + 1) / 2);
-  const size_t smem = ((size_t)m * m + 128) * 8;
-  GDFT_CUDA_TRY(cudaFuncSetAttribute(sym_eig_jacobi_small_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dbg = 0;
-  if (const char* e = getenv("GDFT_EIG_DBG")) dbg = atoi(e);  // timing experiments only (results are wrong when set)
-  sym_eig_jacobi_small_kernel<NB><<<(unsigned)batch, EIG_THREADS, smem, stream>>>(n, A, evals, evecs, dbg);
+  const size_t smem = (size_t)2 * m * m * 8;
+  GDFT_CUDA_TRY((cudaFuncSetAttribute(sym_eig_jacobi_small_kernel<NB, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+  sym_eig_jacobi_small_kernel<NB, NR><<<(unsigned)batch, EIG_THREADS, smem, stream>>>(n, A, evals, evecs);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
@@ -425,8 +454,12 @@ extern "C" int gdft_sym_eigh(gdft_stream_t stream_, int64_t batch, int64_t n, co
   if (!A || !evals || !evecs) return GDFT_BAD_ARGUMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   // items per thread: ceil(npair^2 / 512) blocks, ceil(n * npair / 512) V items
-  if (n <= 44) return launch_eig_small<1>(stream, batch, (int)n, A, evals, evecs);  // npair <= 22: 253 upper blocks on 256 threads
-  if (n <= 64) return launch_eig_small<3>(stream, batch, (int)n, A, evals, evecs);  // npair <= 32: 528 blocks
+  // upper blocks per A thread (256 threads): npair (npair + 1) / 2 <= 253 up to n = 44, <= 528 up to n = 64; V rows per V warp: n / 8
+  if (n <= 16) return launch_eig_small<1, 2>(stream, batch, (int)n, A, evals, evecs);
+  if (n <= 32) return launch_eig_small<1, 4>(stream, batch, (int)n, A, evals, evecs);
+  if (n <= 44) return launch_eig_small<1, 6>(stream, batch, (int)n, A, evals, evecs);
+  if (n <= 48) return launch_eig_small<3, 6>(stream, batch, (int)n, A, evals, evecs);
+  if (n <= 64) return launch_eig_small<3, 8>(stream, batch, (int)n, A, evals, evecs);
   if (n <= 90) return launch_eig<4, 8>(stream, batch, (int)n, A, evals, evecs);
   return launch_eig<6, 11>(stream, batch, (int)n, A, evals, evecs);
 }
