@@ -3,7 +3,7 @@
 // matrices of the H2O/H2-class molecules, where the library path (cuSOLVER syevd: a chain of ~300 tiny kernels,
 // ~1.4 ms for two 43 x 43 matrices, plus a host synchronisation for its status word) dominates the iteration and
 // cannot be captured in a CUDA graph.  One CTA per matrix; A and the accumulated rotations V live in shared memory
-// (n <= 104).  Parallel-order cyclic Jacobi in the Brent-Luk arrangement: the m = 2*ceil(n/2) indices sit in m/2
+// (n <= 90).  Parallel-order cyclic Jacobi in the Brent-Luk arrangement: the m = 2*ceil(n/2) indices sit in m/2
 // adjacent position pairs (2k, 2k+1); a round rotates every pair at once, A <- J^T A J and V <- V J, and then moves
 // rows/columns by ONE FIXED position permutation (the round-robin tournament step), so that after m-1 rounds every
 // index pair has met once and every index is back where it started.  Consequences for the kernel:
@@ -32,7 +32,7 @@ __device__ long long g_eig_prof[8];
 #endif
 
 constexpr int EIG_THREADS = 512;
-constexpr int EIG_MAX_N = 104;
+constexpr int EIG_MAX_N = 90;  // beyond: cuSOLVER through the host framework is faster (n = 104: 3.5 ms vs 6.6 ms)
 constexpr int EIG_MAX_SWEEPS = 40;
 
 // Stop when off(A)^2 <= (n eps)^2 ||A||_F^2: below that the off-diagonal mass is rounding noise of the rotations themselves
@@ -460,6 +460,5 @@ extern "C" int gdft_sym_eigh(gdft_stream_t stream_, int64_t batch, int64_t n, co
   if (n <= 44) return launch_eig_small<1, 6>(stream, batch, (int)n, A, evals, evecs);
   if (n <= 48) return launch_eig_small<3, 6>(stream, batch, (int)n, A, evals, evecs);
   if (n <= 64) return launch_eig_small<3, 8>(stream, batch, (int)n, A, evals, evecs);
-  if (n <= 90) return launch_eig<4, 8>(stream, batch, (int)n, A, evals, evecs);
-  return launch_eig<6, 11>(stream, batch, (int)n, A, evals, evecs);
+  return launch_eig<4, 8>(stream, batch, (int)n, A, evals, evecs);  // 65..90: A and V both in shared memory
 }

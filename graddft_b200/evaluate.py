@@ -60,31 +60,45 @@ def safe_eigh(A: Array) -> Tuple[Array, Array]:
     return _SafeEigh.apply(A)
 
 
-def safe_general_eigh(A: Array, B: Array) -> Tuple[Array, Array]:
-    """grad_dft/utils/eigenproblem.py:110-129: Cholesky-reduced generalised symmetric eigenproblem."""
-    # the _ex / triangular-solve forms are the same factorisations without the status-word round trip to the host
+def overlap_factor(B: Array) -> Array:
+    """inv(L) of the Cholesky factor B = L L^T (eigenproblem.py:125-126).  The overlap matrix does not change inside an SCF
+    loop, so the drivers below factor it once per call instead of once per cycle (XLA hoists the same loop-invariant work
+    out of the reference's fori_loop); the _ex / triangular-solve forms are the factorisations without the status-word
+    round trip to the host."""
     L = torch.linalg.cholesky_ex(B, check_errors=False)[0]
-    L_inv = torch.linalg.solve_triangular(L, torch.eye(L.shape[-1], dtype=L.dtype, device=L.device), upper=False)
+    return torch.linalg.solve_triangular(L, torch.eye(L.shape[-1], dtype=L.dtype, device=L.device), upper=False)
+
+
+def safe_general_eigh(A: Array, B: Array, L_inv: Optional[Array] = None) -> Tuple[Array, Array]:
+    """grad_dft/utils/eigenproblem.py:110-129: Cholesky-reduced generalised symmetric eigenproblem."""
+    if L_inv is None:
+        L_inv = overlap_factor(B)
     C = L_inv @ A @ L_inv.transpose(-1, -2)
     evals, evecs_t = safe_eigh(C)
     return evals, L_inv.transpose(-1, -2) @ evecs_t
 
 
-def safe_fock_solver(fock: Array, overlap: Array) -> Tuple[Array, Array]:
-    """grad_dft/utils/eigenproblem.py:132-149; both spins are solved as one batch."""
-    return safe_general_eigh(fock, overlap)
+def safe_fock_solver(fock: Array, overlap: Array, L_inv: Optional[Array] = None) -> Tuple[Array, Array]:
+    """grad_dft/utils/eigenproblem.py:132-149; both spins are solved as one batch.  `L_inv` = overlap_factor(overlap)
+    when the caller has it already."""
+    return safe_general_eigh(fock, overlap, L_inv)
 
 
 class JittableDiis:
     """grad_dft/evaluate.py:1041-1205 (CDIIS with ring buffers of fixed length)."""
 
-    def __init__(self, overlap_matrix: Array, A: Array, max_diis: int = 8):
+    def __init__(self, overlap_matrix: Array, A: Array, max_diis: int = 8, A_is_identity: bool = False):
         self.overlap_matrix, self.A, self.max_diis = overlap_matrix, A, max_diis
+        # diff_scf_loop passes A = identity (evaluate.py:975): the four products with it are skipped, not computed
+        self.A_is_identity = A_is_identity
 
     def update(self, new_data, diis_data, cycle: int):
         density_matrix, fock_matrix, energy = new_data
         density_vector, fock_vector, energy_vector, error_vector = diis_data
-        fds = torch.einsum("ij,sjk,skl,lm,mn->sin", self.A, fock_matrix, density_matrix, self.overlap_matrix, self.A.T)
+        if self.A_is_identity:
+            fds = fock_matrix @ density_matrix @ self.overlap_matrix
+        else:
+            fds = torch.einsum("ij,sjk,skl,lm,mn->sin", self.A, fock_matrix, density_matrix, self.overlap_matrix, self.A.T)
         error_matrix = fds - fds.transpose(1, 2)
 
         def push(buf, item):
@@ -119,6 +133,8 @@ class JittableDiis:
         _, fock_vector, _, error_vector = diis_data
         x = self.cdiis_minimize(error_vector, cycle)
         F = torch.einsum("si,isjk->sjk", x, fock_vector)
+        if self.A_is_identity:
+            return F, diis_data
         return torch.einsum("ji,sjk,kl->sil", self.A, F, self.A), diis_data
 
 
@@ -135,9 +151,9 @@ def non_scf_predictor(functional: Functional, chunk_size: int = 1024, **kwargs) 
     return predictor
 
 
-def _scf_body(compute_energy, params, molecule: Molecule, fock: Array, *args) -> Tuple[Molecule, Array]:
+def _scf_body(compute_energy, params, molecule: Molecule, fock: Array, *args, L_inv: Optional[Array] = None) -> Tuple[Molecule, Array]:
     """Diagonalise, re-occupy, rebuild rdm1, predict  (evaluate.py:996-1016)."""
-    mo_energy, mo_coeff = safe_fock_solver(fock, molecule.s1e)
+    mo_energy, mo_coeff = safe_fock_solver(fock, molecule.s1e, L_inv)
     molecule = molecule.replace(fock=fock, mo_coeff=mo_coeff, mo_energy=mo_energy)
     molecule = molecule.replace(mo_occ=molecule.get_occ())
     molecule = molecule.replace(rdm1=molecule.make_rdm1())
@@ -157,7 +173,7 @@ def diff_scf_loop(functional: Functional, cycles: int = 25, **kwargs) -> Callabl
         molecule = molecule.replace(fock=fock)
         n = molecule.s1e.shape[0]
         A = torch.eye(n, dtype=molecule.s1e.dtype, device=molecule.s1e.device)
-        diis = JittableDiis(overlap_matrix=molecule.s1e, A=A, max_diis=10)
+        diis = JittableDiis(overlap_matrix=molecule.s1e, A=A, max_diis=10, A_is_identity=True)
 
         def fresh():
             z = torch.zeros((diis.max_diis, 2, n, n), dtype=A.dtype, device=A.device)
@@ -165,9 +181,10 @@ def diff_scf_loop(functional: Functional, cycles: int = 25, **kwargs) -> Callabl
 
         diis_data = fresh()
         norm_gorb = None
+        L_inv = overlap_factor(molecule.s1e)  # loop-invariant
         for cycle in range(cycles):
             fock, diis_data = diis.run((molecule.rdm1, molecule.fock, predicted_e), diis_data, cycle)
-            molecule, predicted_e = _scf_body(compute_energy, params, molecule, fock, *args)
+            molecule, predicted_e = _scf_body(compute_energy, params, molecule, fock, *args, L_inv=L_inv)
             norm_gorb = torch.linalg.norm(molecule.get_mo_grads())
         # evaluate.py:1021-1031 runs one more body with fresh DIIS data and then unpacks `final_state`, i.e. discards
         # it; nothing observable depends on that extra iteration, so it is not executed here.
@@ -187,9 +204,10 @@ def diff_simple_scf_loop(functional: Functional, cycles: int = 25, mixing_factor
     def simple_scf_jitted_iterator(params, atoms: Molecule, *args) -> Molecule:
         predicted_e, fock = compute_energy(params, atoms, *args)
         atoms = atoms.replace(fock=fock, energy=predicted_e)
+        L_inv = overlap_factor(atoms.s1e)  # loop-invariant
         for _ in range(cycles):
             old_rdm1 = atoms.rdm1
-            mo_energy, mo_coeff = safe_fock_solver(atoms.fock, atoms.s1e)
+            mo_energy, mo_coeff = safe_fock_solver(atoms.fock, atoms.s1e, L_inv)
             atoms = atoms.replace(mo_coeff=mo_coeff, mo_energy=mo_energy)
             atoms = atoms.replace(mo_occ=atoms.get_occ())
             rdm1 = (1 - mixing_factor) * old_rdm1 + mixing_factor * atoms.make_rdm1()

@@ -269,7 +269,7 @@ def test_residual_layernorm_elu(cuda_device, N, W, with_res, with_ybias):
     assert not ops.residual_layernorm_elu_supported(dl[0])  # outside a first-order build the composite is used
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 12, 43, 64, 97, 104])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 12, 31, 43, 44, 45, 63, 64, 65, 77, 90])
 def test_sym_eigh_jacobi(cuda_device, n):
     """Row f1: the small symmetric eigenproblem of the SCF iteration (utils/eigenproblem.py:26-106) against LAPACK on the
     CPU: ascending eigenvalues, orthonormal eigenvectors, small residual; degenerate and diagonal inputs included."""
