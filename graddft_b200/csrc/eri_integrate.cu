@@ -11,22 +11,24 @@ namespace gdft {
 // ERI stream is the only global traffic that matters.
 // ---------------------------------------------------------------------------------------------------
 constexpr int ERI_THREADS = 256;
-constexpr int ERI_ROWS_PER_WARP = 4;
-constexpr int ERI_ROWS_PER_CTA = 8 * ERI_ROWS_PER_WARP;
 constexpr int ERI_CHUNK = 2048;
 
-template <bool VEC>
+// RPW rows per warp: 4 for large tensors (P chunk reused by four rows per shared-memory read); 1 for the small ones
+// (n = 43: 1849 rows are 58 CTAs at four rows per warp, a latency-bound 59 us for 27 MB; one row per warp gives 232 CTAs).
+// The per-row summation order (lane-strided columns in chunk order, then the warp tree) is the same for both.
+template <bool VEC, int RPW>
 __global__ void __launch_bounds__(ERI_THREADS) eri_j_kernel(int64_t R, int64_t C, const double* __restrict__ eri,
                                                            const double* __restrict__ P, double* __restrict__ J) {
+  constexpr int ROWS_PER_CTA = 8 * RPW;
   __shared__ __align__(16) double sP[ERI_CHUNK];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t nblocks = (R + ERI_ROWS_PER_CTA - 1) / ERI_ROWS_PER_CTA;
+  const int64_t nblocks = (R + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
   for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-    const int64_t row_base = blk * ERI_ROWS_PER_CTA + warp * ERI_ROWS_PER_WARP;
-    double acc[ERI_ROWS_PER_WARP];
-    const double* rowp[ERI_ROWS_PER_WARP];
+    const int64_t row_base = blk * ROWS_PER_CTA + warp * RPW;
+    double acc[RPW];
+    const double* rowp[RPW];
 #pragma unroll
-    for (int i = 0; i < ERI_ROWS_PER_WARP; i++) {
+    for (int i = 0; i < RPW; i++) {
       acc[i] = 0.0;
       const int64_t row = row_base + i < R ? row_base + i : R - 1;  // clamp: duplicates are discarded below
       rowp[i] = eri + row * C;
@@ -38,26 +40,26 @@ __global__ void __launch_bounds__(ERI_THREADS) eri_j_kernel(int64_t R, int64_t C
       __syncthreads();
       if (VEC) {
         const int len2 = len >> 1;  // C even => len even
-#pragma unroll 2
+#pragma unroll(RPW == 1 ? 8 : 2)
         for (int i = lane; i < len2; i += 32) {
           const double2 pv = reinterpret_cast<const double2*>(sP)[i];
-          double2 e[ERI_ROWS_PER_WARP];
+          double2 e[RPW];
 #pragma unroll
-          for (int q = 0; q < ERI_ROWS_PER_WARP; q++) e[q] = __ldcs(reinterpret_cast<const double2*>(rowp[q] + c0) + i);
+          for (int q = 0; q < RPW; q++) e[q] = __ldcs(reinterpret_cast<const double2*>(rowp[q] + c0) + i);
 #pragma unroll
-          for (int q = 0; q < ERI_ROWS_PER_WARP; q++) acc[q] = fma(e[q].x, pv.x, fma(e[q].y, pv.y, acc[q]));
+          for (int q = 0; q < RPW; q++) acc[q] = fma(e[q].x, pv.x, fma(e[q].y, pv.y, acc[q]));
         }
       } else {
-#pragma unroll 2
+#pragma unroll(RPW == 1 ? 8 : 2)
         for (int i = lane; i < len; i += 32) {
           const double pv = sP[i];
 #pragma unroll
-          for (int q = 0; q < ERI_ROWS_PER_WARP; q++) acc[q] = fma(__ldcs(rowp[q] + c0 + i), pv, acc[q]);
+          for (int q = 0; q < RPW; q++) acc[q] = fma(__ldcs(rowp[q] + c0 + i), pv, acc[q]);
         }
       }
     }
 #pragma unroll
-    for (int q = 0; q < ERI_ROWS_PER_WARP; q++) {
+    for (int q = 0; q < RPW; q++) {
       const double s = warp_sum(acc[q]);
       if (lane == 0 && row_base + q < R) J[row_base + q] = s;
     }
@@ -271,10 +273,16 @@ using namespace gdft;
 static int eri_j_rows_launch(cudaStream_t stream, int64_t n, int64_t rows, const double* eri_rows, const double* P, double* J_rows) {
   const int64_t C = n * n;
   const bool vec = (C % 2 == 0) && aligned16(eri_rows);
-  const int64_t nblocks = (rows + ERI_ROWS_PER_CTA - 1) / ERI_ROWS_PER_CTA;
+  const bool small = (rows + 31) / 32 < 2 * 148;  // fewer than two CTAs per SM at four rows per warp
+  const int64_t nblocks = small ? (rows + 7) / 8 : (rows + 31) / 32;
   const unsigned grid = (unsigned)imin64(nblocks, 148 * 8);
-  if (vec) eri_j_kernel<true><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
-  else eri_j_kernel<false><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
+  if (small) {
+    if (vec) eri_j_kernel<true, 1><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
+    else eri_j_kernel<false, 1><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
+  } else {
+    if (vec) eri_j_kernel<true, 4><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
+    else eri_j_kernel<false, 4><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
+  }
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
