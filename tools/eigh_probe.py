@@ -5,7 +5,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 from graddft_b200 import ops
 dev = torch.device("cuda:0")
-for n in (12, 43, 64, 72, 88, 104):
+for n in (2, 12, 43, 64, 72, 90):
     g = torch.Generator().manual_seed(n)
     A = torch.randn(2, n, n, generator=g, dtype=torch.float64)
     A = (A + A.transpose(1, 2)).to(dev)
