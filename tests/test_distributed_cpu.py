@@ -148,3 +148,43 @@ def test_allreduce_sum_packed_world2_gloo():
             assert torch.allclose(r[2][k], tot, rtol=0, atol=1e-15)
     for r in res:  # the skipped entry is passed through untouched
         assert torch.equal(r[2][2], torch.full((3, 3), 5.0, dtype=torch.float64))
+
+
+def _spin_split_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from graddft_b200 import evaluate
+    g = torch.Generator().manual_seed(5)  # the same replicated inputs on every rank
+    n = 9
+    F = torch.randn(2, n, n, generator=g, dtype=torch.float64)
+    F = F + F.transpose(1, 2)
+    S = torch.randn(n, n, generator=g, dtype=torch.float64)
+    S = torch.eye(n, dtype=torch.float64) + 0.05 * (S + S.T)
+    shard = gdist.GridShard(None, rank, world)
+    with torch.no_grad():
+        w, C = evaluate.safe_fock_solver(F, S, None, shard)     # spin blocks split between the ranks
+        w0, C0 = evaluate.safe_fock_solver(F, S)                # every rank solves both
+    q.put((rank, w.clone(), C.clone(), w0.clone(), C0.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_spin_split_fock_solver_gloo(world):
+    """The sharded SCF iteration's eigensolve: rank 0 solves spin 0, rank 1 spin 1, one all-reduce with a single non-zero
+    contributor per entry -- every rank ends with the bits the unsplit solver produces (host logic; gloo on CPU)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_spin_split_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, w, C, w0, C0 in res:
+        assert torch.equal(w, res[0][1]) and torch.equal(C, res[0][2])      # replicated bit for bit
+        assert torch.allclose(w, w0, rtol=0, atol=1e-13)
+        assert torch.allclose(C.abs(), C0.abs(), rtol=0, atol=1e-10)        # eigenvector signs are the solver's choice
