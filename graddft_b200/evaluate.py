@@ -124,11 +124,16 @@ class JittableDiis:
             fds = torch.einsum("ij,sjk,skl,lm,mn->sin", self.A, fock_matrix, density_matrix, self.overlap_matrix, self.A.T)
         error_matrix = fds - fds.transpose(1, 2)
 
+        # without autograd the ring buffers are private to the loop (created by it, consumed by the next cycle only):
+        # the slot is written in place instead of cloning the whole buffer first
+        in_place = not (torch.is_grad_enabled() and (fock_matrix.requires_grad or density_matrix.requires_grad or density_vector.requires_grad))
+
         def push(buf, item):
             if cycle > self.max_diis:
                 return torch.cat((buf, item.unsqueeze(0)), dim=0)[1:]
             if cycle < buf.shape[0]:  # .at[cycle].set(...): an out-of-bounds index is dropped (cycle == max_diis)
-                buf = buf.clone()
+                if not in_place:
+                    buf = buf.clone()
                 buf[cycle] = item
             return buf
 
@@ -137,7 +142,8 @@ class JittableDiis:
 
     def cdiis_minimize(self, error_vector: Array, cycle: int) -> Array:
         m = error_vector.shape[0]
-        G = torch.einsum("iskl,jskl->sij", error_vector, error_vector)
+        fused = error_vector.is_cuda and not (torch.is_grad_enabled() and error_vector.requires_grad)
+        G = ops.diis_gram(error_vector) if fused else torch.einsum("iskl,jskl->sij", error_vector, error_vector)
         B = torch.zeros((2, m + 1, m + 1), dtype=G.dtype, device=G.device)
         B[:, 1:, 1:] = G
         live = (torch.arange(m, device=G.device) <= cycle).to(G.dtype)
@@ -155,7 +161,10 @@ class JittableDiis:
         diis_data = self.update(new_data, diis_data, cycle)
         _, fock_vector, _, error_vector = diis_data
         x = self.cdiis_minimize(error_vector, cycle)
-        F = torch.einsum("si,isjk->sjk", x, fock_vector)
+        if fock_vector.is_cuda and not (torch.is_grad_enabled() and (x.requires_grad or fock_vector.requires_grad)):
+            F = ops.diis_combine(x, fock_vector)
+        else:
+            F = torch.einsum("si,isjk->sjk", x, fock_vector)
         if self.A_is_identity:
             return F, diis_data
         return torch.einsum("ji,sjk,kl->sil", self.A, F, self.A), diis_data

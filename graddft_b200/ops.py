@@ -576,6 +576,24 @@ def sym_eigh(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return evals, evecs
 
 
+def diis_gram(err_vec: torch.Tensor) -> torch.Tensor:
+    """einsum("iskl,jskl->sij", err_vec, err_vec) for the CDIIS ring buffer err_vec[m, 2, n, n] (no autograd)."""
+    e = _c(err_vec.detach())
+    m, n = int(e.shape[0]), int(e.shape[-1])
+    gram = torch.empty((2, m, m), dtype=F64, device=e.device)
+    check(lib().gdft_diis_gram(stream_ptr(), m, n, ptr(e), ptr(gram)), "gdft_diis_gram")
+    return gram
+
+
+def diis_combine(x: torch.Tensor, fock_vec: torch.Tensor) -> torch.Tensor:
+    """einsum("si,isjk->sjk", x, fock_vec) for x[2, m] and the ring buffer fock_vec[m, 2, n, n] (no autograd)."""
+    x, f = _c(x.detach()), _c(fock_vec.detach())
+    m, n = int(f.shape[0]), int(f.shape[-1])
+    out = torch.empty((2, n, n), dtype=F64, device=f.device)
+    check(lib().gdft_diis_combine(stream_ptr(), m, n, ptr(x), ptr(f), ptr(out)), "gdft_diis_combine")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 # chi generation tail (row f4)
 # ---------------------------------------------------------------------------------------------------------

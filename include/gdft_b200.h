@@ -213,6 +213,13 @@ int gdft_dense_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const doub
 int gdft_sym_eigh_max_n(void);
 int gdft_sym_eigh(gdft_stream_t stream, int64_t batch, int64_t n, const double* A, double* evals, double* evecs);
 
+/* The two reductions of the CDIIS step (grad_dft/evaluate.py:1165 "iskl,jskl->sij" and :1198 "si,isjk->sjk") over the ring
+ * buffers err_vec / fock_vec [m,2,n,n]: gram[2,m,m] (symmetric, deterministic summation order) and the extrapolated
+ * out[2,n,n] = sum_i x[s,i] fock_vec[i,s].  As degenerate GEMMs they cost 21 us each inside the H2O-shaped iteration. */
+int gdft_diis_gram(gdft_stream_t stream, int m, int64_t n, const double* err_vec, double* gram);
+int gdft_diis_combine(gdft_stream_t stream, int m, int64_t n, const double* x /*[2,m]*/, const double* fock_vec,
+                      double* out /*[2,n,n]*/);
+
 /* ---- chi generation tail ----------------------------------------------
  * chi[r, s, a] = sum_{b,d} rdm1[s,b,d] ao[r,b] nu[r,d,a] for the Nc grid points of one nu chunk and one
  * range-separation parameter: the "...bd,b,da->...a" einsum that generate_chi_tensor vmaps over a chunk

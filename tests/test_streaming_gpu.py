@@ -292,3 +292,17 @@ def test_sym_eigh_jacobi(cuda_device, n):
     resid = (A @ V - V * w.unsqueeze(1)).abs().amax(dim=(1, 2))
     assert bool((resid <= 1e-13 * scale * max(n, 4)).all())
     assert not ops.sym_eigh_supported(torch.zeros(2, 200, 200, dtype=F64, device=cuda_device))
+
+
+@pytest.mark.parametrize("m,n", [(10, 43), (10, 7), (3, 64), (10, 264)])
+def test_diis_reductions(cuda_device, m, n):
+    """The two CDIIS reductions (grad_dft/evaluate.py:1165, 1198) against the einsums they replace."""
+    g = torch.Generator().manual_seed(m * 1000 + n)
+    e = torch.randn(m, 2, n, n, generator=g, dtype=F64)
+    e[m - 1] = 0.0  # a dead ring slot, as in the first cycles
+    f = torch.randn(m, 2, n, n, generator=g, dtype=F64)
+    x = torch.randn(2, m, generator=g, dtype=F64)
+    G = ops.diis_gram(e.to(cuda_device))
+    assert relerr(G, torch.einsum("iskl,jskl->sij", e, e)) < 1e-13
+    assert torch.equal(G, G.transpose(1, 2))
+    assert relerr(ops.diis_combine(x.to(cuda_device), f.to(cuda_device)), torch.einsum("si,isjk->sjk", x, f)) < 1e-13
