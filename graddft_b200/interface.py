@@ -58,6 +58,7 @@ class _Uploader:
         self.pinned = [torch.empty((chunk, n, n), dtype=F64).pin_memory() for _ in range(2)]
         self.dev = [torch.empty((chunk, n, n), dtype=F64, device=device) for _ in range(2)]
         self.free = [None, None]  # event recorded after the kernel that consumed dev[i]
+        self.keep = [None, None]
         self.k = 0
         self.h2d_bytes = 0
 
@@ -68,9 +69,14 @@ class _Uploader:
         m = src.shape[0]
         if self.free[i] is not None:
             self.free[i].synchronize()  # the pinned buffer is also reused: the host must not overwrite it early
-        self.pinned[i][:m].copy_(src)
+        if src.is_pinned() and src.is_contiguous():
+            staged = src                # the provider already wrote into page-locked memory: no staging copy
+            self.keep[i] = src          # alive until the copy has been consumed
+        else:
+            self.pinned[i][:m].copy_(src)
+            staged = self.pinned[i][:m]
         with torch.cuda.stream(self.copy_stream):
-            self.dev[i][:m].copy_(self.pinned[i][:m], non_blocking=True)
+            self.dev[i][:m].copy_(staged, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record()
         torch.cuda.current_stream(self.device).wait_event(ready)

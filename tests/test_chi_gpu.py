@@ -21,7 +21,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])  # a: n = 10 (128-bit path), b: n = 7 (odd n: scalar path)
-@pytest.mark.parametrize("where", ["device", "host"])
+@pytest.mark.parametrize("where", ["device", "host", "pinned"])
 def test_generate_chi_tensor_golden(cuda_device, tag, where):
     z = np.load(G / "io_chi.npz")
     t = lambda k: torch.from_numpy(z[f"{tag}_{k}"])  # noqa: E731
@@ -32,7 +32,9 @@ def test_generate_chi_tensor_golden(cuda_device, tag, where):
     def nu_fn(coords, omega):
         calls.append(len(coords))
         nu = provider(coords, omega)
-        return nu.to(cuda_device) if where == "device" else nu.numpy()
+        if where == "device":
+            return nu.to(cuda_device)
+        return nu.contiguous().pin_memory() if where == "pinned" else nu.numpy()
 
     chunk = int(z[f"{tag}_chunk"])
     chi = interface.generate_chi_tensor(t("rdm1").to(cuda_device), t("ao").to(cuda_device), t("coords").to(cuda_device), nu_fn,
