@@ -155,3 +155,50 @@ extern "C" void gdft_ln_elu_bwd_xla(gdft_stream_t s, void** b, const char* opaqu
                            d.ws_bytes);
   finish(rc, (cudaStream_t)s, b[6]);
 }
+// operands: y, ybias, res, scale, bias (flags bit 0: res present, bit 1: ybias present) | results: out, stats
+extern "C" void gdft_dense_ln_elu_fwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_dense_ln_elu_fwd(s, d.N, d.n, (const double*)b[0], (d.flags & 2) ? (const double*)b[1] : nullptr,
+                                 (d.flags & 1) ? (const double*)b[2] : nullptr, (const double*)b[3], (const double*)b[4], d.clip,
+                                 (double*)b[5], (double*)b[6]);
+  finish(rc, (cudaStream_t)s, b[5]);
+}
+// operands: y, ybias, res, scale, bias, stats, out_bar | results: z_bar, scale_bar, bias_bar, ybias_bar, ws
+extern "C" void gdft_dense_ln_elu_bwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_dense_ln_elu_bwd(s, d.N, d.n, (const double*)b[0], (d.flags & 2) ? (const double*)b[1] : nullptr,
+                                 (d.flags & 1) ? (const double*)b[2] : nullptr, (const double*)b[3], (const double*)b[4],
+                                 (const double*)b[5], (const double*)b[6], (double*)b[7], (double*)b[8], (double*)b[9],
+                                 (d.flags & 2) ? (double*)b[10] : nullptr, b[11], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[7]);
+}
+// operands: A[batch = N, n, n] | results: evals[N, n], evecs[N, n, n]
+extern "C" void gdft_sym_eigh_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_sym_eigh(s, d.N, d.n, (const double*)b[0], (double*)b[1], (double*)b[2]);
+  finish(rc, (cudaStream_t)s, b[1]);
+}
+// operands: ao[N, n] (rows of the chunk), rdm1[2, n, n], nu[N, n, n] | results: chi[N, 2, n]   (one omega, one chunk)
+extern "C" void gdft_chi_contract_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_chi_contract(s, d.N, d.n, (const double*)b[0], d.n, (const double*)b[1], (const double*)b[2], (double*)b[3], 2 * d.n);
+  finish(rc, (cudaStream_t)s, b[3]);
+}
+// operands: err_vec[m = W, 2, n, n] | results: gram[2, m, m]
+extern "C" void gdft_diis_gram_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_diis_gram(s, d.W, d.n, (const double*)b[0], (double*)b[1]);
+  finish(rc, (cudaStream_t)s, b[1]);
+}
+// operands: x[2, m = W], fock_vec[m, 2, n, n] | results: out[2, n, n]
+extern "C" void gdft_diis_combine_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_diis_combine(s, d.W, d.n, (const double*)b[0], (const double*)b[1], (double*)b[2]);
+  finish(rc, (cudaStream_t)s, b[2]);
+}

@@ -29,7 +29,8 @@ except ImportError:  # the only supported state here
     HAVE_JAX = False
 
 _TARGETS = ("density_fwd", "density_bwd", "hf_fock", "eri_j", "eri_j_transpose", "xc_integrate_fwd", "xc_integrate_bwd",
-            "pointwise_fwd", "pointwise_bwd", "pointwise_bwd2", "eri_j_rows", "eri_j_transpose_rows", "ln_elu_fwd", "ln_elu_bwd")
+            "pointwise_fwd", "pointwise_bwd", "pointwise_bwd2", "eri_j_rows", "eri_j_transpose_rows", "ln_elu_fwd", "ln_elu_bwd",
+            "dense_ln_elu_fwd", "dense_ln_elu_bwd", "sym_eigh", "chi_contract", "diis_gram", "diis_combine")
 # struct XlaDims { int64 N, n, F, c_rows; int32 flags, nplanes, W, id; double clip; uint64 ws_bytes; }  (jax_ffi.cu)
 _DIMS = struct.Struct("<qqqqiiiidQ")
 

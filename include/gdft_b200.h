@@ -261,6 +261,12 @@ void gdft_eri_j_rows_xla(gdft_stream_t stream, void** buffers, const char* opaqu
 void gdft_eri_j_transpose_rows_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_ln_elu_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_ln_elu_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_dense_ln_elu_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_dense_ln_elu_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_sym_eigh_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_chi_contract_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_diis_gram_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_diis_combine_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 
 #ifdef __cplusplus
 }
