@@ -64,3 +64,25 @@ extern "C" int gdft_diis_combine(gdft_stream_t stream, int m, int64_t n, const d
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
+
+// abs_clip (grad_dft/molecule.py:687-689): out = |src| > thr ? x : 0.  With x = src it is the clip itself; with x = the
+// incoming cotangent it is its VJP (and, applied again, the VJP of that).  The host-framework composite is four launches
+// (abs, compare, zeros_like, where) per call and three more in its reverse pass; the predictor calls it on the
+// densities and on the Fock matrix of every build.
+namespace gdft {
+__global__ void __launch_bounds__(256) abs_clip_kernel(int64_t count, const double* __restrict__ x, const double* __restrict__ src, double thr,
+                                                      double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = fabs(src[i]) > thr ? x[i] : 0.0;
+}
+}  // namespace gdft
+
+extern "C" int gdft_abs_clip(gdft_stream_t stream, int64_t count, const double* x, const double* src, double thr, double* out) {
+  if (count < 0) return GDFT_BAD_SHAPE;
+  if (count == 0) return GDFT_OK;
+  if (!x || !src || !out) return GDFT_BAD_ARGUMENT;
+  const unsigned grid = (unsigned)imin64((count + 255) / 256, 148 * 16);
+  gdft::abs_clip_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(count, x, src, thr, out);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}

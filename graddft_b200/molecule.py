@@ -75,7 +75,9 @@ def _check(name: str, t: Array, ndim: int) -> None:
 # free functions  (grad_dft/molecule.py:341-889)
 # ---------------------------------------------------------------------------------------------------------
 def abs_clip(arr: Array, threshold: float) -> Array:
-    """grad_dft/molecule.py:687-689."""
+    """grad_dft/molecule.py:687-689.  One kernel for float64 CUDA tensors (value and VJP); the composite otherwise."""
+    if arr.is_cuda and arr.dtype == torch.float64:
+        return ops.abs_clip(arr, threshold)
     return torch.where(arr.abs() > threshold, arr, torch.zeros_like(arr))
 
 

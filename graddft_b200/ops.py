@@ -576,6 +576,30 @@ def sym_eigh(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return evals, evecs
 
 
+class _AbsClip(Function):
+    """out = where(|src| > thr, x, 0): abs_clip for x = src, and the same mask applied to a cotangent in its VJP (which is
+    again this Function, so any order of differentiation closes over the one kernel).  No gradient flows to `src`."""
+
+    @staticmethod
+    def forward(ctx, x, src, thr):
+        x, src = _c(x), _c(src)
+        out = torch.empty_like(x)
+        check(lib().gdft_abs_clip(stream_ptr(), x.numel(), ptr(x), ptr(src), float(thr), ptr(out)), "gdft_abs_clip")
+        ctx.save_for_backward(src)
+        ctx.thr = float(thr)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (src,) = ctx.saved_tensors
+        return _AbsClip.apply(g, src, ctx.thr), None, None
+
+
+def abs_clip(arr: torch.Tensor, threshold: float) -> torch.Tensor:
+    """grad_dft/molecule.py:687-689 as one kernel (value and VJP)."""
+    return _AbsClip.apply(arr, arr.detach(), threshold)
+
+
 def diis_gram(err_vec: torch.Tensor) -> torch.Tensor:
     """einsum("iskl,jskl->sij", err_vec, err_vec) for the CDIIS ring buffer err_vec[m, 2, n, n] (no autograd)."""
     e = _c(err_vec.detach())

@@ -220,6 +220,10 @@ int gdft_diis_gram(gdft_stream_t stream, int m, int64_t n, const double* err_vec
 int gdft_diis_combine(gdft_stream_t stream, int m, int64_t n, const double* x /*[2,m]*/, const double* fock_vec,
                       double* out /*[2,n,n]*/);
 
+/* abs_clip (grad_dft/molecule.py:687-689) and its VJP in one elementwise pass: out[i] = |src[i]| > thr ? x[i] : 0
+ * (x = src: the clip; x = a cotangent: the cotangent of the clip's input).  NaN in src gives 0, as jnp.where does. */
+int gdft_abs_clip(gdft_stream_t stream, int64_t count, const double* x, const double* src, double thr, double* out);
+
 /* ---- chi generation tail ----------------------------------------------
  * chi[r, s, a] = sum_{b,d} rdm1[s,b,d] ao[r,b] nu[r,d,a] for the Nc grid points of one nu chunk and one
  * range-separation parameter: the "...bd,b,da->...a" einsum that generate_chi_tensor vmaps over a chunk

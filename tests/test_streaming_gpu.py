@@ -306,3 +306,25 @@ def test_diis_reductions(cuda_device, m, n):
     assert relerr(G, torch.einsum("iskl,jskl->sij", e, e)) < 1e-13
     assert torch.equal(G, G.transpose(1, 2))
     assert relerr(ops.diis_combine(x.to(cuda_device), f.to(cuda_device)), torch.einsum("si,isjk->sjk", x, f)) < 1e-13
+
+
+def test_abs_clip_kernel(cuda_device):
+    """abs_clip (grad_dft/molecule.py:687-689): value, VJP and the VJP of the VJP against the torch composite."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1000, 3, generator=g, dtype=F64)
+    x[::7] *= 1e-31
+    x[5, 1] = 0.0
+    x[6, 2] = float("nan")
+    cot = torch.randn(1000, 3, generator=g, dtype=F64)
+    ref_in = x.clone().requires_grad_(True)
+    ref = torch.where(ref_in.abs() > 1e-30, ref_in, torch.zeros_like(ref_in))
+    (ref_g,) = torch.autograd.grad((ref * cot).sum(), ref_in)
+    xin = x.to(cuda_device).requires_grad_(True)
+    from graddft_b200.molecule import abs_clip
+    out = abs_clip(xin, 1e-30)
+    assert torch.equal(out.detach().cpu(), ref.detach())
+    c = cot.to(cuda_device).requires_grad_(True)
+    (gx,) = torch.autograd.grad((out * c).sum(), xin, create_graph=True)
+    assert torch.equal(gx.detach().cpu(), ref_g)
+    (gc,) = torch.autograd.grad(gx.sum(), c)   # second order: d/dc of mask * c
+    assert torch.equal(gc.cpu(), (x.abs() > 1e-30).to(F64))
