@@ -55,6 +55,7 @@ SIGNATURES = {
     "gdft_sym_eigh": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "gdft_abs_clip": (c_int, [_P, c_int64, _P, _P, c_double, _P]),
     "gdft_diis_gram": (c_int, [_P, c_int, c_int64, _P, _P]),
+    "gdft_diis_matrix": (c_int, [_P, c_int, c_int64, c_int, _P, _P]),
     "gdft_diis_combine": (c_int, [_P, c_int, c_int64, _P, _P, _P]),
     "gdft_chi_contract_max_n": (c_int64, []),
     "gdft_chi_contract": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, _P, _P, c_int64]),

@@ -9,7 +9,11 @@
 
 namespace gdft {
 
-__global__ void __launch_bounds__(256) diis_gram_kernel(int m, int64_t nn, const double* __restrict__ e, double* __restrict__ gram) {
+// BORDERED: write the CDIIS matrix B[2, m+1, m+1] of evaluate.py:1167-1181 instead of the bare Gram matrix:
+// B[0,0] = 0, B[0,1+i] = B[1+i,0] = live_i, B[1+i,1+j] = G_ij, and B[1+i,1+i] = 1 for the slots that are not live yet
+// (live_i = i <= cycle).
+template <bool BORDERED>
+__global__ void __launch_bounds__(256) diis_gram_kernel(int m, int64_t nn, int cycle, const double* __restrict__ e, double* __restrict__ gram) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int total = 2 * m * m;
   if (warp >= total) return;
@@ -26,8 +30,21 @@ __global__ void __launch_bounds__(256) diis_gram_kernel(int m, int64_t nn, const
   for (; k < nn; k += 32) acc[0] = fma(a[k], b[k], acc[0]);
   const double v = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
   if (lane == 0) {
-    gram[((size_t)s * m + i) * m + j] = v;
-    gram[((size_t)s * m + j) * m + i] = v;
+    if (BORDERED) {
+      const int mb = m + 1;
+      double* B = gram + (size_t)s * mb * mb;
+      const bool live = i <= cycle;
+      B[(1 + i) * mb + 1 + j] = (i == j && !live) ? 1.0 : v;
+      B[(1 + j) * mb + 1 + i] = (i == j && !live) ? 1.0 : v;
+      if (i == j) {
+        B[1 + i] = live ? 1.0 : 0.0;
+        B[(1 + i) * mb] = live ? 1.0 : 0.0;
+        if (i == 0) B[0] = 0.0;
+      }
+    } else {
+      gram[((size_t)s * m + i) * m + j] = v;
+      gram[((size_t)s * m + j) * m + i] = v;
+    }
   }
 }
 
@@ -50,7 +67,17 @@ extern "C" int gdft_diis_gram(gdft_stream_t stream, int m, int64_t n, const doub
   if (m <= 0 || m > 64 || n <= 0 || n > 32768) return GDFT_BAD_SHAPE;
   if (!err || !gram) return GDFT_BAD_ARGUMENT;
   const int warps = 2 * m * m;
-  diis_gram_kernel<<<(warps * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, n * n, err, gram);
+  diis_gram_kernel<false><<<(warps * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, n * n, 0, err, gram);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+extern "C" int gdft_diis_matrix(gdft_stream_t stream, int m, int64_t n, int cycle, const double* err /*[m,2,n,n]*/,
+                                double* B /*[2,m+1,m+1]*/) {
+  if (m <= 0 || m > 64 || n <= 0 || n > 32768) return GDFT_BAD_SHAPE;
+  if (!err || !B) return GDFT_BAD_ARGUMENT;
+  const int warps = 2 * m * m;
+  diis_gram_kernel<true><<<(warps * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, n * n, cycle, err, B);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }

@@ -143,7 +143,16 @@ class JittableDiis:
     def cdiis_minimize(self, error_vector: Array, cycle: int) -> Array:
         m = error_vector.shape[0]
         fused = error_vector.is_cuda and not (torch.is_grad_enabled() and error_vector.requires_grad)
-        G = ops.diis_gram(error_vector) if fused else torch.einsum("iskl,jskl->sij", error_vector, error_vector)
+        if fused:  # Gram matrix, border, live mask and diagonal fix-up in one kernel; the right-hand side is a constant
+            B = ops.diis_matrix(error_vector, cycle)
+            C = self.__dict__.get("_rhs")
+            if C is None or C.shape[1] != m + 1 or C.device != B.device:
+                C = torch.zeros((2, m + 1), dtype=B.dtype, device=B.device)
+                C[:, 0] = 1
+                self._rhs = C
+            x = (torch.linalg.inv_ex(B, check_errors=False)[0] @ C.unsqueeze(-1)).squeeze(-1)
+            return x[:, 1:]
+        G = torch.einsum("iskl,jskl->sij", error_vector, error_vector)
         B = torch.zeros((2, m + 1, m + 1), dtype=G.dtype, device=G.device)
         B[:, 1:, 1:] = G
         live = (torch.arange(m, device=G.device) <= cycle).to(G.dtype)

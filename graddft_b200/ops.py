@@ -609,6 +609,15 @@ def diis_gram(err_vec: torch.Tensor) -> torch.Tensor:
     return gram
 
 
+def diis_matrix(err_vec: torch.Tensor, cycle: int) -> torch.Tensor:
+    """The bordered CDIIS matrix B[2, m+1, m+1] (grad_dft/evaluate.py:1167-1181) from the ring buffer err_vec[m, 2, n, n]."""
+    e = _c(err_vec.detach())
+    m, n = int(e.shape[0]), int(e.shape[-1])
+    B = torch.empty((2, m + 1, m + 1), dtype=F64, device=e.device)
+    check(lib().gdft_diis_matrix(stream_ptr(), m, n, int(cycle), ptr(e), ptr(B)), "gdft_diis_matrix")
+    return B
+
+
 def diis_combine(x: torch.Tensor, fock_vec: torch.Tensor) -> torch.Tensor:
     """einsum("si,isjk->sjk", x, fock_vec) for x[2, m] and the ring buffer fock_vec[m, 2, n, n] (no autograd)."""
     x, f = _c(x.detach()), _c(fock_vec.detach())

@@ -217,6 +217,9 @@ int gdft_sym_eigh(gdft_stream_t stream, int64_t batch, int64_t n, const double* 
  * buffers err_vec / fock_vec [m,2,n,n]: gram[2,m,m] (symmetric, deterministic summation order) and the extrapolated
  * out[2,n,n] = sum_i x[s,i] fock_vec[i,s].  As degenerate GEMMs they cost 21 us each inside the H2O-shaped iteration. */
 int gdft_diis_gram(gdft_stream_t stream, int m, int64_t n, const double* err_vec, double* gram);
+/* The bordered CDIIS matrix of evaluate.py:1167-1181 straight from the ring buffer: B[s,0,0] = 0, B[s,0,1+i] = B[s,1+i,0] =
+ * (i <= cycle), B[s,1+i,1+j] = gram[s,i,j], with 1 on the diagonal of the slots that are not live yet. */
+int gdft_diis_matrix(gdft_stream_t stream, int m, int64_t n, int cycle, const double* err_vec, double* B /*[2,m+1,m+1]*/);
 int gdft_diis_combine(gdft_stream_t stream, int m, int64_t n, const double* x /*[2,m]*/, const double* fock_vec,
                       double* out /*[2,n,n]*/);
 

@@ -328,3 +328,27 @@ def test_abs_clip_kernel(cuda_device):
     assert torch.equal(gx.detach().cpu(), ref_g)
     (gc,) = torch.autograd.grad(gx.sum(), c)   # second order: d/dc of mask * c
     assert torch.equal(gc.cpu(), (x.abs() > 1e-30).to(F64))
+
+
+@pytest.mark.parametrize("cycle", [0, 3, 9, 10, 14])
+def test_diis_bordered_matrix(cuda_device, cycle):
+    """gdft_diis_matrix against the assembly of grad_dft/evaluate.py:1167-1181 as the host mirror spells it out."""
+    from graddft_b200.evaluate import JittableDiis
+    m, n = 10, 13
+    g = torch.Generator().manual_seed(cycle)
+    e = torch.randn(m, 2, n, n, generator=g, dtype=F64)
+    e[min(cycle, m - 1) + 1:] = 0.0
+    B = ops.diis_matrix(e.to(cuda_device), cycle).cpu()
+    G = torch.einsum("iskl,jskl->sij", e, e)
+    ref = torch.zeros((2, m + 1, m + 1), dtype=F64)
+    ref[:, 1:, 1:] = G
+    live = (torch.arange(m) <= cycle).to(F64)
+    ref[:, 0, 1:] = live
+    ref[:, 1:, 0] = live
+    idx = torch.arange(1, m + 1)
+    ref[:, idx, idx] = torch.where(live.bool(), torch.diagonal(G, dim1=1, dim2=2), torch.ones_like(live))
+    assert relerr(B, ref) < 1e-13
+    d = JittableDiis(torch.eye(n, dtype=F64, device=cuda_device), torch.eye(n, dtype=F64, device=cuda_device), m)
+    x_fused = d.cdiis_minimize(e.to(cuda_device), cycle)
+    x_ref = (torch.linalg.inv(ref) @ torch.tensor([1.0] + [0.0] * m, dtype=F64))[:, 1:]
+    assert relerr(x_fused, x_ref) < 1e-9
