@@ -50,7 +50,7 @@ SIGNATURES = {
     "gdft_ln_elu_fwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, c_double, _P, _P]),
     "gdft_ln_elu_bwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_dense_ln_elu_fwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, c_double, _P, _P]),
-    "gdft_dense_ln_elu_bwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "gdft_dense_ln_elu_bwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_sym_eigh_max_n": (c_int, []),
     "gdft_sym_eigh": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "gdft_abs_clip": (c_int, [_P, c_int64, _P, _P, c_double, _P]),

@@ -164,15 +164,15 @@ extern "C" void gdft_dense_ln_elu_fwd_xla(gdft_stream_t s, void** b, const char*
                                  (double*)b[5], (double*)b[6]);
   finish(rc, (cudaStream_t)s, b[5]);
 }
-// operands: y, ybias, res, scale, bias, stats, out_bar | results: z_bar, scale_bar, bias_bar, ybias_bar, ws
+// operands: y, ybias, res, scale, bias, stats, fwd_out, out_bar | results: z_bar, scale_bar, bias_bar, ybias_bar, ws
 extern "C" void gdft_dense_ln_elu_bwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
   XlaDims d;
   if (!dims_ok(opaque, len, &d)) return;
   int rc = gdft_dense_ln_elu_bwd(s, d.N, d.n, (const double*)b[0], (d.flags & 2) ? (const double*)b[1] : nullptr,
                                  (d.flags & 1) ? (const double*)b[2] : nullptr, (const double*)b[3], (const double*)b[4],
-                                 (const double*)b[5], (const double*)b[6], (double*)b[7], (double*)b[8], (double*)b[9],
-                                 (d.flags & 2) ? (double*)b[10] : nullptr, b[11], d.ws_bytes);
-  finish(rc, (cudaStream_t)s, b[7]);
+                                 (const double*)b[5], (d.flags & 4) ? (const double*)b[6] : nullptr, (const double*)b[7], (double*)b[8],
+                                 (double*)b[9], (double*)b[10], (d.flags & 2) ? (double*)b[11] : nullptr, b[12], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[8]);
 }
 // operands: A[batch = N, n, n] | results: evals[N, n], evecs[N, n, n]
 extern "C" void gdft_sym_eigh_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {

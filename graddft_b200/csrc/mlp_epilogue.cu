@@ -23,13 +23,16 @@ struct LnArgs {
   int64_t N;
   int W;
   double eps;
-  const double *y, *ybias, *res, *gamma, *beta, *stats_in, *dout;
+  const double *y, *ybias, *res, *gamma, *beta, *stats_in, *dout, *fwd_out;
   double *out, *stats_out, *dz, *partial;
 };
 
 __device__ __forceinline__ double elu_val(double o) { return o > 0.0 ? o : expm1(o); }
 __device__ __forceinline__ double elu_der(double o) { return o > 0.0 ? 1.0 : exp(o); }
 
+// MAXV = double2 per lane the row needs (W <= 64 * MAXV): sizing the register arrays for W = 512 when W = 256 cost the
+// reverse pass 205 registers per thread, one CTA per SM and a latency-bound 41 % of DRAM bandwidth (ncu)
+template <int MAXV>
 __global__ void __launch_bounds__(LN_THREADS) ln_elu_fwd_kernel(const LnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = a.W >> 1;
@@ -37,10 +40,10 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_fwd_kernel(const LnArgs a) 
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < a.N; row += (int64_t)gridDim.x * LN_WARPS) {
     const double2* y2 = reinterpret_cast<const double2*>(a.y + row * a.W);
     const double2* r2 = a.res ? reinterpret_cast<const double2*>(a.res + row * a.W) : nullptr;
-    double2 z[LN_MAXV];
+    double2 z[MAXV];
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < MAXV; i++) {
       const int c = lane + 32 * i;
       z[i] = make_double2(0.0, 0.0);
       if (c < nv) {
@@ -53,13 +56,13 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_fwd_kernel(const LnArgs a) 
     const double mean = warp_sum(s) * inv_w;
     double v = 0.0;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < MAXV; i++) {
       if (lane + 32 * i < nv) { const double dx = z[i].x - mean, dy = z[i].y - mean; v += dx * dx + dy * dy; }
     }
     const double rstd = 1.0 / sqrt(warp_sum(v) * inv_w + a.eps);
     double2* o2 = reinterpret_cast<double2*>(a.out + row * a.W);
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < MAXV; i++) {
       const int c = lane + 32 * i;
       if (c < nv) {
         const double2 g = reinterpret_cast<const double2*>(a.gamma)[c], b = reinterpret_cast<const double2*>(a.beta)[c];
@@ -70,25 +73,25 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_fwd_kernel(const LnArgs a) 
   }
 }
 
-template <bool PARAM_GRADS>
-__global__ void __launch_bounds__(LN_THREADS) ln_elu_bwd_kernel(const LnArgs a) {
+template <bool PARAM_GRADS, int MAXV>
+__global__ void __launch_bounds__(LN_THREADS, MAXV <= 4 ? 2 : 1) ln_elu_bwd_kernel(const LnArgs a) {
   extern __shared__ __align__(16) double sred[];  // [LN_WARPS][3][W] when PARAM_GRADS
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = a.W >> 1;
   const double inv_w = 1.0 / a.W;
-  double2 pg[LN_MAXV], pb[LN_MAXV], pz[LN_MAXV];  // column sums: scale_bar, bias_bar, and z_bar (= the Dense bias cotangent)
+  double2 pg[MAXV], pb[MAXV], pz[MAXV];  // column sums: scale_bar, bias_bar, and z_bar (= the Dense bias cotangent)
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; i++) pg[i] = pb[i] = pz[i] = make_double2(0.0, 0.0);
+  for (int i = 0; i < MAXV; i++) pg[i] = pb[i] = pz[i] = make_double2(0.0, 0.0);
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < a.N; row += (int64_t)gridDim.x * LN_WARPS) {
     const double2* y2 = reinterpret_cast<const double2*>(a.y + row * a.W);
     const double2* r2 = a.res ? reinterpret_cast<const double2*>(a.res + row * a.W) : nullptr;
     const double2* d2 = reinterpret_cast<const double2*>(a.dout + row * a.W);
     const double2 st = reinterpret_cast<const double2*>(a.stats_in)[row];
     const double mean = st.x, rstd = st.y;
-    double2 nrm[LN_MAXV], dn[LN_MAXV];
+    double2 nrm[MAXV], dn[MAXV];
     double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < MAXV; i++) {
       const int c = lane + 32 * i;
       nrm[i] = dn[i] = make_double2(0.0, 0.0);
       if (c < nv) {
@@ -98,7 +101,17 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_bwd_kernel(const LnArgs a) 
         const double2 g = reinterpret_cast<const double2*>(a.gamma)[c], b = reinterpret_cast<const double2*>(a.beta)[c];
         const double2 dy = __ldcs(d2 + c);
         nrm[i] = make_double2((z.x - mean) * rstd, (z.y - mean) * rstd);
-        const double dox = dy.x * elu_der(nrm[i].x * g.x + b.x), doy = dy.y * elu_der(nrm[i].y * g.y + b.y);
+        double dox, doy;
+        if (a.fwd_out) {
+          // elu'(o) from the forward OUTPUT: out > 0 <=> o > 0, and for o <= 0 out = expm1(o), so exp(o) = out + 1 -- one more
+          // 8-byte read per element instead of an FP64 exp (the reverse pass is FP64-pipe-bound, not HBM-bound, with it)
+          const double2 fo = __ldcs(reinterpret_cast<const double2*>(a.fwd_out + row * a.W) + c);
+          dox = dy.x * (fo.x > 0.0 ? 1.0 : fo.x + 1.0);
+          doy = dy.y * (fo.y > 0.0 ? 1.0 : fo.y + 1.0);
+        } else {
+          dox = dy.x * elu_der(nrm[i].x * g.x + b.x);
+          doy = dy.y * elu_der(nrm[i].y * g.y + b.y);
+        }
         if (PARAM_GRADS) {
           pg[i].x = fma(dox, nrm[i].x, pg[i].x); pg[i].y = fma(doy, nrm[i].y, pg[i].y);
           pb[i].x += dox; pb[i].y += doy;
@@ -111,7 +124,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_bwd_kernel(const LnArgs a) 
     const double m1 = warp_sum(s1) * inv_w, m2 = warp_sum(s2) * inv_w;
     double2* z2 = reinterpret_cast<double2*>(a.dz + row * a.W);
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < MAXV; i++) {
       const int c = lane + 32 * i;
       if (c < nv) {
         const double2 zb = make_double2(rstd * (dn[i].x - m1 - nrm[i].x * m2), rstd * (dn[i].y - m1 - nrm[i].y * m2));
@@ -123,7 +136,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_elu_bwd_kernel(const LnArgs a) 
   if (PARAM_GRADS) {
     double2* s2p = reinterpret_cast<double2*>(sred);
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < MAXV; i++) {
       const int c = lane + 32 * i;
       if (c < nv) { s2p[(warp * 3 + 0) * nv + c] = pg[i]; s2p[(warp * 3 + 1) * nv + c] = pb[i]; s2p[(warp * 3 + 2) * nv + c] = pz[i]; }
     }
@@ -193,7 +206,10 @@ extern "C" int gdft_dense_ln_elu_fwd(gdft_stream_t stream, int64_t N, int64_t W,
     return GDFT_BAD_ALIGNMENT;
   LnArgs a{};
   a.N = N; a.W = (int)W; a.eps = eps; a.y = y; a.ybias = ybias; a.res = res; a.gamma = scale; a.beta = bias; a.out = out; a.stats_out = stats;
-  ln_elu_fwd_kernel<<<ln_grid(N), LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (W <= 128) ln_elu_fwd_kernel<2><<<ln_grid(N), LN_THREADS, 0, st>>>(a);
+  else if (W <= 256) ln_elu_fwd_kernel<4><<<ln_grid(N), LN_THREADS, 0, st>>>(a);
+  else ln_elu_fwd_kernel<8><<<ln_grid(N), LN_THREADS, 0, st>>>(a);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
@@ -204,31 +220,42 @@ extern "C" int gdft_ln_elu_fwd(gdft_stream_t stream, int64_t N, int64_t W, const
 }
 
 extern "C" int gdft_dense_ln_elu_bwd(gdft_stream_t stream_, int64_t N, int64_t W, const double* y, const double* ybias, const double* res,
-                                     const double* scale, const double* bias, const double* stats, const double* out_bar, double* z_bar,
-                                     double* scale_bar, double* bias_bar, double* ybias_bar, void* ws, size_t ws_bytes) {
+                                     const double* scale, const double* bias, const double* stats, const double* fwd_out,
+                                     const double* out_bar, double* z_bar, double* scale_bar, double* bias_bar, double* ybias_bar, void* ws,
+                                     size_t ws_bytes) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = ln_check(N, W)) return rc;
   if (!y || !scale || !bias || !stats || !out_bar || !z_bar) return GDFT_BAD_ARGUMENT;
   if (!aligned16(y) || !aligned16(ybias) || !aligned16(res) || !aligned16(scale) || !aligned16(bias) || !aligned16(stats) ||
-      !aligned16(out_bar) || !aligned16(z_bar) || !aligned16(ws))
+      !aligned16(fwd_out) || !aligned16(out_bar) || !aligned16(z_bar) || !aligned16(ws))
     return GDFT_BAD_ALIGNMENT;
   const bool pgrads = scale_bar || bias_bar || ybias_bar;
   if (pgrads && ws_bytes < ln_elu_workspace(N, W)) return GDFT_WORKSPACE_TOO_SMALL;
   LnArgs a{};
   a.N = N; a.W = (int)W; a.y = y; a.ybias = ybias; a.res = res; a.gamma = scale; a.beta = bias; a.stats_in = stats; a.dout = out_bar;
-  a.dz = z_bar;
+  a.dz = z_bar; a.fwd_out = fwd_out;
   a.partial = static_cast<double*>(ws);
   const int grid = ln_grid(N);
   if (pgrads) {
     const size_t smem = (size_t)LN_WARPS * 3 * W * 8;
-    GDFT_CUDA_TRY(cudaFuncSetAttribute(ln_elu_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ln_elu_bwd_kernel<true><<<grid, LN_THREADS, smem, stream>>>(a);
+    if (W <= 128) {
+      GDFT_CUDA_TRY((cudaFuncSetAttribute(ln_elu_bwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+      ln_elu_bwd_kernel<true, 2><<<grid, LN_THREADS, smem, stream>>>(a);
+    } else if (W <= 256) {
+      GDFT_CUDA_TRY((cudaFuncSetAttribute(ln_elu_bwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+      ln_elu_bwd_kernel<true, 4><<<grid, LN_THREADS, smem, stream>>>(a);
+    } else {
+      GDFT_CUDA_TRY((cudaFuncSetAttribute(ln_elu_bwd_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+      ln_elu_bwd_kernel<true, 8><<<grid, LN_THREADS, smem, stream>>>(a);
+    }
     GDFT_LAUNCH_CHECK();
     ln_param_reduce_kernel<<<(unsigned)((3 * W + LNR_OUT - 1) / LNR_OUT), LNR_OUT * LNR_G, 0, stream>>>(grid, (int)W, a.partial, scale_bar,
                                                                                                       bias_bar, ybias_bar);
     GDFT_LAUNCH_CHECK();
   } else {
-    ln_elu_bwd_kernel<false><<<grid, LN_THREADS, 0, stream>>>(a);
+    if (W <= 128) ln_elu_bwd_kernel<false, 2><<<grid, LN_THREADS, 0, stream>>>(a);
+    else if (W <= 256) ln_elu_bwd_kernel<false, 4><<<grid, LN_THREADS, 0, stream>>>(a);
+    else ln_elu_bwd_kernel<false, 8><<<grid, LN_THREADS, 0, stream>>>(a);
     GDFT_LAUNCH_CHECK();
   }
   return GDFT_OK;
@@ -237,5 +264,6 @@ extern "C" int gdft_dense_ln_elu_bwd(gdft_stream_t stream_, int64_t N, int64_t W
 extern "C" int gdft_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* res, const double* scale,
                                const double* bias, const double* stats, const double* out_bar, double* z_bar, double* scale_bar,
                                double* bias_bar, void* ws, size_t ws_bytes) {
-  return gdft_dense_ln_elu_bwd(stream, N, W, y, nullptr, res, scale, bias, stats, out_bar, z_bar, scale_bar, bias_bar, nullptr, ws, ws_bytes);
+  return gdft_dense_ln_elu_bwd(stream, N, W, y, nullptr, res, scale, bias, stats, nullptr, out_bar, z_bar, scale_bar, bias_bar, nullptr, ws,
+                               ws_bytes);
 }

@@ -499,14 +499,14 @@ class _ResidualLayerNormElu(Function):
         with _timed("gdft_ln_elu_fwd"):
             check(L.gdft_dense_ln_elu_fwd(stream_ptr(), N, W, ptr(y), ptr(ybias), ptr(res), ptr(scale), ptr(bias), float(eps), ptr(out),
                                           ptr(stats)), "gdft_dense_ln_elu_fwd")
-        ctx.save_for_backward(y, ybias, res, scale, bias, stats)
+        ctx.save_for_backward(y, ybias, res, scale, bias, stats, out)  # `out` is the next layer's saved input anyway
         ctx.eps = float(eps)
         return out
 
     @staticmethod
     @once_differentiable  # second order goes through the composite path, chosen up front by the caller
     def backward(ctx, out_bar):
-        y, ybias, res, scale, bias, stats = ctx.saved_tensors
+        y, ybias, res, scale, bias, stats, fwd_out = ctx.saved_tensors
         L = lib()
         N, W = int(y.shape[0]), int(y.shape[1])
         need = ctx.needs_input_grad
@@ -518,7 +518,7 @@ class _ResidualLayerNormElu(Function):
         ws = workspace(L.gdft_workspace_bytes(_lib.OP_LN_ELU, N, W, 0, 0), y.device) if pg else None
         with _timed("gdft_ln_elu_bwd"):
             check(L.gdft_dense_ln_elu_bwd(stream_ptr(), N, W, ptr(y), ptr(ybias), ptr(res), ptr(scale), ptr(bias), ptr(stats),
-                                          ptr(_c(out_bar)), ptr(zbar), ptr(sbar), ptr(bbar), ptr(ybbar), wptr(ws),
+                                          ptr(fwd_out), ptr(_c(out_bar)), ptr(zbar), ptr(sbar), ptr(bbar), ptr(ybbar), wptr(ws),
                                           ws.numel() if ws is not None else 0), "gdft_dense_ln_elu_bwd")
         return (zbar if need[0] else None), ybbar, (zbar if (res is not None and need[2]) else None), sbar, bbar, None
 

@@ -202,6 +202,7 @@ int gdft_dense_ln_elu_fwd(gdft_stream_t stream, int64_t N, int64_t W, const doub
                           double* stats);
 int gdft_dense_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const double* y, const double* ybias,
                           const double* res, const double* scale, const double* bias, const double* stats,
+                          const double* fwd_out /*the forward output, or NULL: elu' is then recomputed with exp*/,
                           const double* out_bar, double* z_bar, double* scale_bar, double* bias_bar,
                           double* ybias_bar, void* ws, size_t ws_bytes);
 
