@@ -87,11 +87,22 @@ def _spin_split_eigh(C: Array, shard) -> Tuple[Array, Array]:
     return buf[:, :n].contiguous(), buf[:, n:].reshape(2, n, n).contiguous()
 
 
-def safe_general_eigh(A: Array, B: Array, L_inv: Optional[Array] = None, shard=None) -> Tuple[Array, Array]:
-    """grad_dft/utils/eigenproblem.py:110-129: Cholesky-reduced generalised symmetric eigenproblem."""
+WARM_RESTART_EVERY = 8  # cold Jacobi start every so many cycles: V_k = V_{k-1} V'_k accumulates round-off in its orthogonality
+
+
+def safe_general_eigh(A: Array, B: Array, L_inv: Optional[Array] = None, shard=None, warm: Optional[dict] = None) -> Tuple[Array, Array]:
+    """grad_dft/utils/eigenproblem.py:110-129: Cholesky-reduced generalised symmetric eigenproblem.  `warm` is the SCF
+    loop's per-call state: without autograd, and for matrices the small Jacobi kernel takes, the eigenvectors of the
+    previous cycle warm-start the sweeps (the result is the decomposition of C either way; only the sweep count changes)."""
     if L_inv is None:
         L_inv = overlap_factor(B)
     C = L_inv @ A @ L_inv.transpose(-1, -2)
+    if (warm is not None and C.shape[-1] <= 64 and ops.sym_eigh_supported(C)
+            and not (torch.is_grad_enabled() and C.requires_grad)):
+        uses = warm.get("uses", 0)
+        evals, evecs_t = ops.sym_eigh(C, warm.get("V") if uses % WARM_RESTART_EVERY else None)
+        warm["V"], warm["uses"] = evecs_t, uses + 1
+        return evals, L_inv.transpose(-1, -2) @ evecs_t
     if (shard is not None and shard.world >= 2 and C.dim() == 3 and C.shape[0] == 2 and not ops.sym_eigh_supported(C)
             and not (torch.is_grad_enabled() and C.requires_grad)):
         evals, evecs_t = _spin_split_eigh(C, shard)
@@ -100,11 +111,11 @@ def safe_general_eigh(A: Array, B: Array, L_inv: Optional[Array] = None, shard=N
     return evals, L_inv.transpose(-1, -2) @ evecs_t
 
 
-def safe_fock_solver(fock: Array, overlap: Array, L_inv: Optional[Array] = None, shard=None) -> Tuple[Array, Array]:
+def safe_fock_solver(fock: Array, overlap: Array, L_inv: Optional[Array] = None, shard=None, warm: Optional[dict] = None) -> Tuple[Array, Array]:
     """grad_dft/utils/eigenproblem.py:132-149; both spins are solved as one batch.  `L_inv` = overlap_factor(overlap)
     when the caller has it already; `shard` (a distributed.GridShard) lets the ranks of a grid-sharded molecule split
     the two spin blocks between them."""
-    return safe_general_eigh(fock, overlap, L_inv, shard)
+    return safe_general_eigh(fock, overlap, L_inv, shard, warm)
 
 
 class JittableDiis:
@@ -192,9 +203,10 @@ def non_scf_predictor(functional: Functional, chunk_size: int = 1024, **kwargs) 
     return predictor
 
 
-def _scf_body(compute_energy, params, molecule: Molecule, fock: Array, *args, L_inv: Optional[Array] = None) -> Tuple[Molecule, Array]:
+def _scf_body(compute_energy, params, molecule: Molecule, fock: Array, *args, L_inv: Optional[Array] = None,
+              warm: Optional[dict] = None) -> Tuple[Molecule, Array]:
     """Diagonalise, re-occupy, rebuild rdm1, predict  (evaluate.py:996-1016)."""
-    mo_energy, mo_coeff = safe_fock_solver(fock, molecule.s1e, L_inv, molecule.__dict__.get("_shard"))
+    mo_energy, mo_coeff = safe_fock_solver(fock, molecule.s1e, L_inv, molecule.__dict__.get("_shard"), warm)
     molecule = molecule.replace(fock=fock, mo_coeff=mo_coeff, mo_energy=mo_energy)
     molecule = molecule.replace(mo_occ=molecule.get_occ())
     molecule = molecule.replace(rdm1=molecule.make_rdm1())
@@ -223,9 +235,10 @@ def diff_scf_loop(functional: Functional, cycles: int = 25, **kwargs) -> Callabl
         diis_data = fresh()
         norm_gorb = None
         L_inv = overlap_factor(molecule.s1e)  # loop-invariant
+        warm = {}  # eigenvectors of the previous cycle (Jacobi warm start)
         for cycle in range(cycles):
             fock, diis_data = diis.run((molecule.rdm1, molecule.fock, predicted_e), diis_data, cycle)
-            molecule, predicted_e = _scf_body(compute_energy, params, molecule, fock, *args, L_inv=L_inv)
+            molecule, predicted_e = _scf_body(compute_energy, params, molecule, fock, *args, L_inv=L_inv, warm=warm)
             norm_gorb = torch.linalg.norm(molecule.get_mo_grads())
         # evaluate.py:1021-1031 runs one more body with fresh DIIS data and then unpacks `final_state`, i.e. discards
         # it; nothing observable depends on that extra iteration, so it is not executed here.
@@ -246,9 +259,10 @@ def diff_simple_scf_loop(functional: Functional, cycles: int = 25, mixing_factor
         predicted_e, fock = compute_energy(params, atoms, *args)
         atoms = atoms.replace(fock=fock, energy=predicted_e)
         L_inv = overlap_factor(atoms.s1e)  # loop-invariant
+        warm = {}
         for _ in range(cycles):
             old_rdm1 = atoms.rdm1
-            mo_energy, mo_coeff = safe_fock_solver(atoms.fock, atoms.s1e, L_inv, atoms.__dict__.get("_shard"))
+            mo_energy, mo_coeff = safe_fock_solver(atoms.fock, atoms.s1e, L_inv, atoms.__dict__.get("_shard"), warm)
             atoms = atoms.replace(mo_coeff=mo_coeff, mo_energy=mo_energy)
             atoms = atoms.replace(mo_occ=atoms.get_occ())
             rdm1 = (1 - mixing_factor) * old_rdm1 + mixing_factor * atoms.make_rdm1()

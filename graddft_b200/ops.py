@@ -563,16 +563,21 @@ def sym_eigh_supported(A: torch.Tensor) -> bool:
     return A.is_cuda and A.dtype == F64 and A.dim() >= 2 and A.shape[-1] == A.shape[-2] and 0 < A.shape[-1] <= lib().gdft_sym_eigh_max_n()
 
 
-def sym_eigh(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def sym_eigh(A: torch.Tensor, V0: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(eigenvalues ascending [..., n], eigenvectors as columns [..., n, n]) of symmetric A[..., n, n]; no autograd
-    (evaluate.safe_eigh supplies the VJP), no host synchronisation."""
+    (evaluate.safe_eigh supplies the VJP), no host synchronisation.  `V0` (same shape, ORTHOGONAL: the eigenvectors of a
+    nearby matrix) warm-starts the Jacobi sweeps."""
     A = _c(A.detach())
     n = int(A.shape[-1])
     batch = A.numel() // (n * n)
     evals = torch.empty(A.shape[:-1], dtype=F64, device=A.device)
     evecs = torch.empty_like(A)
+    if V0 is not None:
+        V0 = _c(V0.detach())
+        if V0.shape != A.shape:
+            raise TypeError(f"V0 {tuple(V0.shape)} does not match A {tuple(A.shape)}")
     with _timed("gdft_sym_eigh"):
-        check(lib().gdft_sym_eigh(stream_ptr(), batch, n, ptr(A), ptr(evals), ptr(evecs)), "gdft_sym_eigh")
+        check(lib().gdft_sym_eigh_warm(stream_ptr(), batch, n, ptr(A), ptr(V0), ptr(evals), ptr(evecs)), "gdft_sym_eigh_warm")
     return evals, evecs
 
 

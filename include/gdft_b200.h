@@ -213,6 +213,11 @@ int gdft_dense_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const doub
  * together with the rest of the SCF iteration.  Larger matrices stay with the host framework's cuSOLVER path. */
 int gdft_sym_eigh_max_n(void);
 int gdft_sym_eigh(gdft_stream_t stream, int64_t batch, int64_t n, const double* A, double* evals, double* evecs);
+/* Warm start: V0[b, n, n] orthogonal (the eigenvectors of the previous SCF cycle; NULL = cold).  The sweeps run on
+ * V0^T A V0, which is nearly diagonal once the SCF settles, and the eigenvectors returned are V0 V'.  Used for n <= 64;
+ * larger n ignore V0.  The result is the eigen-decomposition of A either way; only the sweep count changes. */
+int gdft_sym_eigh_warm(gdft_stream_t stream, int64_t batch, int64_t n, const double* A, const double* V0, double* evals,
+                       double* evecs);
 
 /* The two reductions of the CDIIS step (grad_dft/evaluate.py:1165 "iskl,jskl->sij" and :1198 "si,isjk->sjk") over the ring
  * buffers err_vec / fock_vec [m,2,n,n]: gram[2,m,m] (symmetric, deterministic summation order) and the extrapolated

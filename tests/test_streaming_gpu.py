@@ -352,3 +352,25 @@ def test_diis_bordered_matrix(cuda_device, cycle):
     x_fused = d.cdiis_minimize(e.to(cuda_device), cycle)
     x_ref = (torch.linalg.inv(ref) @ torch.tensor([1.0] + [0.0] * m, dtype=F64))[:, 1:]
     assert relerr(x_fused, x_ref) < 1e-9
+
+
+@pytest.mark.parametrize("n", [2, 5, 12, 43, 44, 63, 64])
+def test_sym_eigh_warm_start(cuda_device, n):
+    """gdft_sym_eigh_warm: with the eigenvectors of a nearby matrix as V0 the decomposition of A is the same (eigenvalues to
+    1e-13, A V = V diag(w), V orthogonal), also when V0 already diagonalises A exactly and when it is unrelated to A."""
+    g = torch.Generator().manual_seed(100 + n)
+    A = torch.randn(2, n, n, generator=g, dtype=F64)
+    A = A + A.transpose(1, 2)
+    P = torch.randn(2, n, n, generator=g, dtype=F64)
+    A2 = A + 1e-3 * (P + P.transpose(1, 2))
+    w_ref = torch.linalg.eigvalsh(A2)
+    Ad, A2d = A.to(cuda_device), A2.to(cuda_device)
+    _, V_prev = ops.sym_eigh(Ad)
+    Q, _ = torch.linalg.qr(torch.randn(2, n, n, generator=g, dtype=F64))
+    for V0 in (V_prev, ops.sym_eigh(A2d)[1], Q.to(cuda_device)):
+        w, V = ops.sym_eigh(A2d, V0)
+        assert float((w.cpu() - w_ref).abs().max()) < 1e-12 * float(w_ref.abs().max())
+        resid = (A2d @ V - V * w.unsqueeze(-2)).abs().max()
+        assert float(resid) < 1e-12 * float(w_ref.abs().max())
+        eye = torch.eye(n, dtype=F64, device=cuda_device)
+        assert float((V.transpose(1, 2) @ V - eye).abs().max()) < 1e-12
