@@ -87,6 +87,56 @@ def _spin_split_eigh(C: Array, shard) -> Tuple[Array, Array]:
     return buf[:, :n].contiguous(), buf[:, n:].reshape(2, n, n).contiguous()
 
 
+REFINE_MAX_ITER = 5
+REFINE_FIRST_STEP = 1e-2  # a first correction larger than this is refused at once
+REFINE_GATE = 1e-5        # relative change of the matrix since the previous cycle below which refinement is attempted
+REFINE_ACCEPT = 1e-7   # ||E||_F of the last correction; the error after it is its square
+REFINE_RESIDUAL = 1e-14  # times n: bound on ||offdiag(X^T C X)|| / ||C|| and on ||I - X^T X|| of an accepted result
+
+
+def refine_eigh(C: Array, X: Array) -> Tuple[Optional[Array], Optional[Array]]:
+    """Eigen-decomposition of symmetric C[b, n, n] by iterative refinement of approximate eigenvectors X (the previous SCF
+    cycle's), for matrices beyond the Jacobi kernel: T. Ogita, K. Aishima, "Iterative refinement for symmetric eigenvalue
+    decomposition", Japan J. Indust. Appl. Math. 35 (2018), Algorithm 1.  With R = I - X^T X, S = X^T C X and
+    l_i = s_ii / (1 - r_ii):  E_ij = (s_ij + l_j r_ij) / (l_j - l_i) where |l_i - l_j| exceeds
+    delta = 2 (||S - diag(l)|| + ||C|| ||R||), r_ij / 2 otherwise (diagonal and multiple eigenvalues);  X <- X + X E.
+    Quadratically convergent, four n^3 products per step (library GEMMs: this is n x n harness work like DIIS), against
+    ~1000 launch-bound kernels of the library eigensolver (2.8 ms per 264 x 264 matrix).  Returns (eigenvalues ascending,
+    eigenvectors) once the last correction is below REFINE_ACCEPT, else (None, None): the caller then runs the full solver
+    -- X too far from the eigenvectors (first cycles), or a cluster of eigenvalues the step cannot separate."""
+    n = C.shape[-1]
+    eye = torch.eye(n, dtype=C.dtype, device=C.device)
+    normC = torch.linalg.matrix_norm(C).reshape(-1, 1, 1)
+    last = 1.0
+    for it in range(REFINE_MAX_ITER):
+        Xt = X.transpose(-1, -2)
+        R = eye - Xt @ X
+        S = Xt @ (C @ X)
+        lam = torch.diagonal(S, dim1=-2, dim2=-1) / (1.0 - torch.diagonal(R, dim1=-2, dim2=-1))
+        delta = 2.0 * (torch.linalg.matrix_norm(S - torch.diag_embed(lam)).reshape(-1, 1, 1) + normC * torch.linalg.matrix_norm(R).reshape(-1, 1, 1))
+        diff = lam.unsqueeze(-2) - lam.unsqueeze(-1)  # [i, j] = l_j - l_i
+        sep = diff.abs() > delta
+        E = torch.where(sep, (S + lam.unsqueeze(-2) * R) / torch.where(sep, diff, torch.ones_like(diff)), 0.5 * R)
+        X = X + X @ E
+        size = float(torch.linalg.matrix_norm(E).max())  # one host read per step: this path is eager by construction
+        if not (size == size) or size > (REFINE_FIRST_STEP if it == 0 else 0.5 * last):
+            return None, None  # not in the basin of quadratic convergence: leave after one step, not five
+        last = size
+        if size <= REFINE_ACCEPT:
+            # accept only what IS a decomposition: X^T C X diagonal and X orthogonal to working accuracy (pairs the step
+            # treated as one cluster are not rotated against each other, so a small E alone does not prove it)
+            Xt = X.transpose(-1, -2)
+            S = Xt @ (C @ X)
+            lam = torch.diagonal(S, dim1=-2, dim2=-1)
+            bad = torch.maximum(torch.linalg.matrix_norm(S - torch.diag_embed(lam)) / normC.reshape(-1),
+                                torch.linalg.matrix_norm(eye - Xt @ X))
+            if not float(bad.max()) <= REFINE_RESIDUAL * n:
+                return None, None
+            lam, idx = torch.sort(lam, dim=-1)
+            return lam, torch.gather(X, -1, idx.unsqueeze(-2).expand_as(X))
+    return None, None
+
+
 WARM_RESTART_EVERY = 8  # cold Jacobi start every so many cycles: V_k = V_{k-1} V'_k accumulates round-off in its orthogonality
 
 
@@ -102,6 +152,27 @@ def safe_general_eigh(A: Array, B: Array, L_inv: Optional[Array] = None, shard=N
         uses = warm.get("uses", 0)
         evals, evecs_t = ops.sym_eigh(C, warm.get("V") if uses % WARM_RESTART_EVERY else None)
         warm["V"], warm["uses"] = evecs_t, uses + 1
+        return evals, L_inv.transpose(-1, -2) @ evecs_t
+    no_grad = not (torch.is_grad_enabled() and C.requires_grad)
+    if warm is not None and no_grad and C.is_cuda and not ops.sym_eigh_supported(C):
+        # beyond the Jacobi kernel: refine the previous cycle's eigenvectors; the full solver is the fallback
+        # ... attempted only once the SCF has settled: the step needs a change of C well below its smallest eigenvalue
+        # gaps (in the benzene-shaped loop it is accepted from cycle 9 on, 1.2 ms against 5.6 ms, and a refused attempt
+        # costs 0.6 ms), so the relative change of C since the previous cycle gates it
+        prev_C = warm.get("C")
+        warm["C"] = C
+        if warm.get("V") is not None and prev_C is not None and prev_C.shape == C.shape:
+            change = float(torch.linalg.matrix_norm(C - prev_C).max() / torch.linalg.matrix_norm(C).max())
+            if change <= REFINE_GATE:
+                evals, evecs_t = refine_eigh(C, warm["V"])
+                if evals is not None:
+                    warm["V"] = evecs_t
+                    return evals, L_inv.transpose(-1, -2) @ evecs_t
+        if shard is not None and shard.world >= 2 and C.dim() == 3 and C.shape[0] == 2:
+            evals, evecs_t = _spin_split_eigh(C, shard)
+        else:
+            evals, evecs_t = torch.linalg.eigh(C)
+        warm["V"] = evecs_t
         return evals, L_inv.transpose(-1, -2) @ evecs_t
     if (shard is not None and shard.world >= 2 and C.dim() == 3 and C.shape[0] == 2 and not ops.sym_eigh_supported(C)
             and not (torch.is_grad_enabled() and C.requires_grad)):

@@ -374,3 +374,41 @@ def test_sym_eigh_warm_start(cuda_device, n):
         assert float(resid) < 1e-12 * float(w_ref.abs().max())
         eye = torch.eye(n, dtype=F64, device=cuda_device)
         assert float((V.transpose(1, 2) @ V - eye).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("n", [96, 264])
+def test_refine_eigh(cuda_device, n):
+    """evaluate.refine_eigh (Ogita-Aishima refinement of the previous cycle's eigenvectors, n beyond the Jacobi kernel):
+    accepted results are eigen-decompositions to working accuracy -- also with an exactly degenerate pair --, and starts that
+    are too far (an unrelated basis; a perturbation larger than the gaps) are refused, never answered wrongly."""
+    from graddft_b200.evaluate import refine_eigh
+    g = torch.Generator().manual_seed(n)
+    Q, _ = torch.linalg.qr(torch.randn(2, n, n, generator=g, dtype=F64))
+    lam = torch.linspace(-4.0, 5.0, n, dtype=F64).repeat(2, 1) + 0.01 * torch.rand(2, n, generator=g, dtype=F64)
+    lam[:, 5] = lam[:, 4]  # an exactly double eigenvalue
+    A = (Q * lam.unsqueeze(-2)) @ Q.transpose(1, 2)
+    A = 0.5 * (A + A.transpose(1, 2))
+    P = torch.randn(2, n, n, generator=g, dtype=F64)
+    P = P + P.transpose(1, 2)
+    lam2 = lam.clone()
+    lam2[:, 5] += 0.03  # separated spectrum for the perturbed case
+    B = (Q * lam2.unsqueeze(-2)) @ Q.transpose(1, 2)
+    B = 0.5 * (B + B.transpose(1, 2)) + 1e-6 * P
+    eye = torch.eye(n, dtype=F64, device=cuda_device)
+    Qd = Q.to(cuda_device)
+    for M in (A, B):
+        ref = torch.linalg.eigvalsh(M)
+        Md = M.to(cuda_device)
+        w, V = refine_eigh(Md, Qd)
+        assert w is not None
+        scale = float(ref.abs().max())
+        assert float((w.cpu() - ref).abs().max()) < 1e-12 * scale
+        assert float((Md @ V - V * w.unsqueeze(-2)).abs().max()) < 1e-11 * scale
+        assert float((V.transpose(1, 2) @ V - eye).abs().max()) < 1e-12
+    far, _ = torch.linalg.qr(torch.randn(2, n, n, generator=g, dtype=F64))
+    for M, X0 in ((B, far), (B + 1e-2 * P, Q)):
+        w, V = refine_eigh(M.to(cuda_device), X0.to(cuda_device))
+        if w is not None:  # a refusal is the expected outcome; an answer must still be a decomposition
+            Md = M.to(cuda_device)
+            assert float((Md @ V - V * w.unsqueeze(-2)).abs().max()) < 1e-11 * float(w.abs().max())
+    assert refine_eigh(B.to(cuda_device), far.to(cuda_device))[0] is None
