@@ -166,3 +166,40 @@ def test_generate_chi_needs_cuda():
     with pytest.raises(GdftError):
         interface.generate_chi_tensor(torch.zeros(2, 3, 3, dtype=F64), torch.zeros(5, 3, dtype=F64), torch.zeros(5, 3, dtype=F64),
                                       lambda c, o: torch.zeros(len(c), 3, 3, dtype=F64), [0.0])
+
+
+def test_archive_append_and_attrs(tmp_path):
+    """Archive (the h5py stand-in): groups / datasets / attributes / string datasets survive close + reopen, "a" appends,
+    duplicate names are refused, iteration is name-ordered (what h5py does)."""
+    path = str(tmp_path / "x.npz")
+    with interface.Archive(path, "a") as f:
+        g = f.create_group("molecule_b_1")
+        g.create_dataset("ao", data=np.arange(6.0).reshape(2, 3))
+        g.create_dataset("name", data="H2O")
+        g.attrs["type"] = "reactant"
+        f.create_group("empty_group")
+    with interface.Archive(path, "a") as f:
+        f.create_group("molecule_a_0")["energy"] = -1.5
+        with pytest.raises(ValueError):
+            f.create_group("molecule_b_1")
+    with interface.Archive(path, "r") as f:
+        assert [k for k, _ in f.items()] == ["empty_group", "molecule_a_0", "molecule_b_1"]
+        g = f["molecule_b_1"]
+        assert np.array_equal(np.asarray(g["ao"]), np.arange(6.0).reshape(2, 3))
+        assert g["name"][()] == b"H2O" and str(g["name"][()]) == "b'H2O'"   # h5py hands strings back as bytes
+        assert g.attrs["type"] == "reactant"
+        assert float(f["molecule_a_0/energy"][()]) == -1.5
+    with pytest.raises(FileNotFoundError):
+        interface.Archive(str(tmp_path / "missing.npz"), "r")
+
+
+def test_loader_shuffles_only_when_training(tmp_path, golden_molecules, monkeypatch):
+    monkeypatch.setattr(interface, "_h5py", None)
+    water, anon, reaction = golden_molecules
+    interface.saver(str(tmp_path / "d"), reactions=[reaction], molecules=[water, anon])
+    order = [k for k, _ in interface.loader(str(tmp_path / "d"), randomize=True, training=False)]
+    assert order == ["molecule", "molecule", "reaction"]  # name order: no shuffle outside training (pyscf.py:464-465)
+    import random
+    random.seed(3)
+    seen = {tuple(k for k, _ in interface.loader(str(tmp_path / "d"), randomize=True, training=True)) for _ in range(12)}
+    assert len(seen) > 1
