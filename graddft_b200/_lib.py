@@ -113,6 +113,7 @@ def ptr(t: torch.Tensor | None):
         raise TypeError(f"expected float64, got {t.dtype}")
     if not t.is_contiguous():
         raise GdftError("tensor must be contiguous")
+    _same_device(t)
     return c_void_p(t.data_ptr())
 
 
@@ -122,10 +123,21 @@ def wptr(t: torch.Tensor | None):
         return None
     if not t.is_cuda:
         raise GdftError("graddft_b200 kernels need CUDA tensors (there is no CPU path)")
+    _same_device(t)
     return c_void_p(t.data_ptr())
 
 
+def _same_device(t: torch.Tensor) -> None:
+    """The C entry points launch on the CURRENT device's current stream (stream_ptr) and never switch devices, so a
+    tensor living on another GPU would be dereferenced by a kernel running on the wrong device: refuse it here."""
+    cur = torch.cuda.current_device()
+    if t.device.index != cur:
+        raise GdftError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: wrap the call in "
+                        f"`with torch.cuda.device({t.device.index}):` (kernels launch on the current device's current stream)")
+
+
 def stream_ptr() -> c_void_p:
+    """cudaStream_t of the current device's current stream; `ptr`/`wptr` check that every tensor lives on that device."""
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

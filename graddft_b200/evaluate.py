@@ -362,6 +362,7 @@ class _GraphedLoop:
     def __init__(self, loop: Callable):
         self.loop = loop
         self.entries = {}
+        self.last_call_was_graph = False  # whether the most recent call was a graph replay (bench.py reports it)
 
     @staticmethod
     def _tensors(params, molecule):
@@ -380,6 +381,7 @@ class _GraphedLoop:
         wants_grad = torch.is_grad_enabled() and (_requires_grad(params) or molecule.rdm1.requires_grad)
         if (args or wants_grad or not molecule.rdm1.is_cuda or "_shard" in molecule.__dict__
                 or n > ops.lib().gdft_sym_eigh_max_n()):
+            self.last_call_was_graph = False
             return self.loop(params, molecule, *args)
         ts = self._tensors(params, molecule)
         key = tuple((t.data_ptr(), tuple(t.shape)) for t in ts)
@@ -400,6 +402,7 @@ class _GraphedLoop:
                 self.entries.pop(next(iter(self.entries)))
             entry = self.entries[key] = (graph, out, ts)  # `ts` keeps the captured storages alive
         entry[0].replay()
+        self.last_call_was_graph = True
         return entry[1]
 
 

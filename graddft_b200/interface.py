@@ -55,6 +55,10 @@ class _Uploader:
     def __init__(self, device, chunk: int, n: int):
         self.device = device
         self.copy_stream = torch.cuda.Stream(device=device)
+        # the freshly allocated device buffers below may be blocks the caching allocator has just taken back from
+        # kernels still running on the compute stream: the copy stream must not write into them before those finish
+        self.copy_stream.wait_stream(torch.cuda.current_stream(device))
+        self.inflight = None  # copy event of a chunk uploaded straight from the provider's own page-locked buffer
         self.pinned = [torch.empty((chunk, n, n), dtype=F64).pin_memory() for _ in range(2)]
         self.dev = [torch.empty((chunk, n, n), dtype=F64, device=device) for _ in range(2)]
         self.free = [None, None]  # event recorded after the kernel that consumed dev[i]
@@ -80,8 +84,17 @@ class _Uploader:
             ready = torch.cuda.Event()
             ready.record()
         torch.cuda.current_stream(self.device).wait_event(ready)
+        self.inflight = ready if staged is src else None
         self.h2d_bytes += m * src.shape[1] * src.shape[2] * 8
         return self.dev[i][:m], i
+
+    def before_next_chunk(self) -> None:
+        """Called before the provider is asked for the next chunk: a provider that hands over page-locked memory may
+        reuse that one buffer for every chunk, so the upload reading it must have finished (the kernel consuming the
+        device copy keeps running meanwhile)."""
+        if self.inflight is not None:
+            self.inflight.synchronize()
+            self.inflight = None
 
     def consumed(self, i: int) -> None:
         ev = torch.cuda.Event()
@@ -113,6 +126,8 @@ def generate_chi_tensor(rdm1: Array, ao: Array, grid_coords: Array, mol: Any, om
     for w, omega in enumerate(omegas):
         for start in range(0, N, chunk_size):
             end = min(start + chunk_size, N)
+            if up is not None:
+                up.before_next_chunk()
             nu = nu_fn(grid_coords[start:end], omega)
             slot = None
             if not (isinstance(nu, torch.Tensor) and nu.is_cuda):

@@ -266,6 +266,11 @@ def Harris_energy_predictor(functional: Functional, **kwargs) -> Callable:
         energy = (molecule.mo_occ * molecule.mo_energy).sum()
         P = molecule.rdm1.sum(dim=0)
         coulomb_e = -(P * ops.coulomb_j(P, molecule.rep_tensor)).sum() / 2.0
+        # jax.grad of the Harris energy differentiates THROUGH xcfock (the -<rdm1, dV_xc/dtheta> term), so V_xc must keep
+        # its graph whenever anything upstream of it is being differentiated; the first-order tap path of hybrids would
+        # hand back a constant V_xc and is not used then
+        if "create_graph" not in hkwargs:
+            hkwargs["create_graph"] = torch.is_grad_enabled() and (_requires_grad(params) or molecule.rdm1.requires_grad)
         exc, xcfock, _ = xc_energy_and_grads(functional, params, molecule.rdm1, molecule, *args, **hkwargs)
         return energy + exc - (molecule.rdm1 * xcfock).sum() + coulomb_e + molecule.nuclear_repulsion
 

@@ -19,7 +19,7 @@ F64 = torch.float64
 
 __all__ = [
     "CLIP", "abs_clip", "density", "grad_density", "lapl_density", "kinetic_density",
-    "HF_energy_density", "HF_fock", "coulomb_potential", "coulomb_energy", "one_body_energy",
+    "HF_energy_density", "HF_fock", "FactorizedERI", "coulomb_potential", "coulomb_energy", "one_body_energy",
     "nonXC", "make_rdm1", "orbital_grad", "get_occ", "integrate", "xc_energy",
     "exchange_polarization_correction", "correlation_polarization_correction",
     "lsda_x_e", "b88_x_e", "pw92_c_e", "vwn_c_e", "lyp_c_e",
@@ -75,8 +75,28 @@ def HF_fock(chi, g, ao):
     return -0.5 * torch.einsum("rwsc,wsr,ra->wsac", chi, g, ao)
 
 
+class FactorizedERI:
+    """Test-only stand-in for a rep_tensor given in factorised form, (pq|rt) = sum_Q B[Q,p,q] B[Q,r,t] / scale (how the
+    synthetic tensors are built): the contraction of molecule.py:811 without materialising n^4 doubles on the host, so
+    that predictor-level parity can be checked at n = 264 (38.9 GB dense).  `dense(device)` is the tensor itself."""
+
+    def __init__(self, B: torch.Tensor, scale: float):
+        self.B, self.scale = B, float(scale)
+
+    def contract(self, P: torch.Tensor) -> torch.Tensor:
+        return torch.einsum("Qpq,Q->pq", self.B, torch.einsum("Qrt,rt->Q", self.B, P)) / self.scale
+
+    def dense(self, device=None) -> torch.Tensor:
+        B = self.B.to(device) if device is not None else self.B
+        Q, n = B.shape[0], B.shape[1]
+        B2 = B.reshape(Q, n * n)
+        return ((B2.T @ B2) / self.scale).reshape(n, n, n, n)
+
+
 def coulomb_potential(P, rep_tensor):
     """molecule.py:811 -- J[p,q] = sum_rt (pq|rt) P[r,t]."""
+    if isinstance(rep_tensor, FactorizedERI):
+        return rep_tensor.contract(P)
     return torch.einsum("pqrt,rt->pq", rep_tensor, P)
 
 

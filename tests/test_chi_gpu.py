@@ -21,19 +21,23 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])  # a: n = 10 (128-bit path), b: n = 7 (odd n: scalar path)
-@pytest.mark.parametrize("where", ["device", "host", "pinned"])
+@pytest.mark.parametrize("where", ["device", "host", "pinned", "pinned_reused"])
 def test_generate_chi_tensor_golden(cuda_device, tag, where):
     z = np.load(G / "io_chi.npz")
     t = lambda k: torch.from_numpy(z[f"{tag}_{k}"])  # noqa: E731
     n = t("ao").shape[1]
     provider = seeded_nu(n, int(z[f"{tag}_nu_seed"]))
     calls = []
+    reused = torch.empty((int(z[f"{tag}_chunk"]), n, n), dtype=F64).pin_memory()
 
     def nu_fn(coords, omega):
         calls.append(len(coords))
         nu = provider(coords, omega)
         if where == "device":
             return nu.to(cuda_device)
+        if where == "pinned_reused":  # a provider that writes every chunk into the SAME page-locked buffer
+            reused[:len(coords)].copy_(nu)
+            return reused[:len(coords)]
         return nu.contiguous().pin_memory() if where == "pinned" else nu.numpy()
 
     chunk = int(z[f"{tag}_chunk"])

@@ -242,3 +242,36 @@ def test_harris_energy(cuda_device):
                - (mol["rdm1"] * v).sum() + mol["nuclear_repulsion"])
         e = gd.Harris_energy_predictor(FUNCS[name])(None, m)
         assert abs(float(e) - float(ref)) < E_TOL, name
+
+
+def test_harris_energy_parameter_gradient_matches_finite_differences(cuda_device):
+    """jax.grad of the Harris energy (grad_dft/train.py:220-308) differentiates through V_xc: the -<rdm1, dV_xc/dtheta>
+    term must be in the parameter gradient.  Semilocal neural functional and the hybrid DM21 (whose first-order tap path
+    would return a constant V_xc), against central finite differences along a random direction."""
+    dev = cuda_device
+    m = gd.molecule_from_tensors(_gapped_molecule(1200, 8, 1984), dev)
+    semilocal = gd.DM21(layer_widths=(8, 8), nograd_densities=None, densitygrads=None, combine_densities=None,
+                        nograd_coefficient_inputs=None, coefficient_input_grads=None, combine_inputs=None, local_features=1, needs_omegas=None)
+    hybrid = gd.DM21(layer_widths=(8, 8))
+    for fun, nin in ((semilocal, 7), (hybrid, 11)):
+        flat = fun.generate_DM21_weights(n_input_features=nin, seed=3)
+        gen = torch.Generator().manual_seed(5)
+        direction = {k: torch.randn(v.shape, generator=gen, dtype=F64).to(dev) for k, v in flat.items()}
+        harris = gd.Harris_energy_predictor(fun)
+        params = {k: v.to(dev).requires_grad_(True) for k, v in flat.items()}
+        e = harris(params, m)
+        grads = torch.autograd.grad(e, list(params.values()))
+        slope = sum(float((g * direction[k]).sum()) for g, k in zip(grads, params))
+
+        def central(h):
+            with torch.no_grad():
+                ep = harris({k: v.to(dev) + h * direction[k] for k, v in flat.items()}, m)
+                em = harris({k: v.to(dev) - h * direction[k] for k, v in flat.items()}, m)
+            return float(ep - em) / (2 * h)
+
+        fd = (4.0 * central(1e-5) - central(2e-5)) / 3.0
+        assert abs(slope - fd) < 1e-6 * max(1.0, abs(fd)), (slope, fd)
+        # the term that used to be dropped is not negligible here: the E_xc-only slope differs from the full one
+        exc = fun.energy_xc_only(params, m)
+        slope_exc = sum(float((g * direction[k]).sum()) for g, k in zip(torch.autograd.grad(exc, list(params.values())), params))
+        assert abs(slope - slope_exc) > 1e-6 * max(1.0, abs(fd))
