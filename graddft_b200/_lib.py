@@ -54,6 +54,7 @@ SIGNATURES = {
     "gdft_sym_eigh_max_n": (c_int, []),
     "gdft_sym_eigh": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "gdft_sym_eigh_warm": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P]),
+    "gdft_sym_eigh_ex": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "gdft_abs_clip": (c_int, [_P, c_int64, _P, _P, c_double, _P]),
     "gdft_diis_gram": (c_int, [_P, c_int, c_int64, _P, _P]),
     "gdft_diis_matrix": (c_int, [_P, c_int, c_int64, c_int, _P, _P]),

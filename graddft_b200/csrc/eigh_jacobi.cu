@@ -53,7 +53,7 @@ __device__ __forceinline__ int eig_next_pos(int pos, int npair) {
 // NB / NV: 2 x 2 blocks of A and (row, pair) items of V per thread
 template <int NB, int NV>
 __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_kernel(int n, const double* __restrict__ A_in, double* __restrict__ evals,
-                                                                     double* __restrict__ evecs) {
+                                                                     double* __restrict__ evecs, int* __restrict__ info) {
   extern __shared__ __align__(16) double sm[];
   const int npair = (n + 1) / 2, m = 2 * npair;  // m even: every row of sA / sV starts 16-byte aligned
   double* sA = sm;                       // [m][m]
@@ -127,7 +127,11 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_kernel(int n, cons
     __syncthreads();
     if (tid == 0) { double s = 0; for (int w = 0; w < EIG_THREADS / 32; w++) s += red[w]; s_tot = s; }
     __syncthreads();
-    if (!(s_off > eig_tol(n) * s_tot)) break;  // also leaves on NaN
+    if (!(s_off > eig_tol(n) * s_tot)) {  // also leaves on NaN
+      if (tid == 0 && info != nullptr) info[blockIdx.x] = (s_off == s_off && s_tot == s_tot) ? sweep : -2;
+      break;
+    }
+    if (tid == 0 && info != nullptr && sweep == EIG_MAX_SWEEPS - 1) info[blockIdx.x] = -1;  // the bound was hit
 
     for (int r = 0; r < m - 1; r++) {
       // ---- read phase: own blocks and V items into registers; diagonal-block owners publish the rotations ----
@@ -247,7 +251,8 @@ __device__ __forceinline__ void eig_pair_rotation(const double* __restrict__ src
 
 template <int NB, int NR>
 __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n, const double* __restrict__ A_in, const double* __restrict__ V0_in,
-                                                                           double* __restrict__ evals, double* __restrict__ evecs) {
+                                                                           double* __restrict__ evals, double* __restrict__ evecs,
+                                                                           int* __restrict__ info) {
   // warps 0..7 own the 2 x 2 blocks of A, warps 8..15 own the rows of V (NR rows per warp, in registers).
   // Warm start (V0_in != NULL): the sweeps run on A' = V0^T A V0 for an orthogonal V0 -- the eigenvectors of the previous
   // SCF cycle, which leave A' nearly diagonal (off^2/||A||^2 = 8e-3, 1e-4, 1e-6, ... over the cycles of the H2O-shaped
@@ -347,7 +352,11 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
     __syncthreads();
     if (tid == 0) { double s = 0; for (int w = 0; w < NW; w++) s += red[w]; s_tot = s; }
     __syncthreads();
-    if (!(s_off > eig_tol(n) * s_tot)) break;  // also leaves on NaN
+    if (!(s_off > eig_tol(n) * s_tot)) {  // also leaves on NaN
+      if (tid == 0 && info != nullptr) info[blockIdx.x] = (s_off == s_off && s_tot == s_tot) ? sweep : -2;
+      break;
+    }
+    if (tid == 0 && info != nullptr && sweep == EIG_MAX_SWEEPS - 1) info[blockIdx.x] = -1;  // the bound was hit
 
     // Round r: (1) the rotation warp (warp 0, lane = pair) derives the npair rotations from the diagonal blocks of the
     // copy of A being read and publishes them; barrier 0 (all warps); (2) the A warps write the rotated, permuted blocks
@@ -458,11 +467,11 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
 }
 
 template <int NB, int NR>
-static int launch_eig_small(cudaStream_t stream, int64_t batch, int n, const double* A, const double* V0, double* evals, double* evecs) {
+static int launch_eig_small(cudaStream_t stream, int64_t batch, int n, const double* A, const double* V0, double* evals, double* evecs, int* info) {
   const int m = 2 * ((n + 1) / 2);
   const size_t smem = ((size_t)2 * m * m + (V0 ? (size_t)n * n : 0)) * 8;
   GDFT_CUDA_TRY((cudaFuncSetAttribute(sym_eig_jacobi_small_kernel<NB, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)2 * m * m + (size_t)n * n) * 8))));
-  sym_eig_jacobi_small_kernel<NB, NR><<<(unsigned)batch, EIG_THREADS, smem, stream>>>(n, A, V0, evals, evecs);
+  sym_eig_jacobi_small_kernel<NB, NR><<<(unsigned)batch, EIG_THREADS, smem, stream>>>(n, A, V0, evals, evecs, info);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
@@ -473,10 +482,10 @@ static size_t eig_smem(int n) {
 }
 
 template <int NB, int NV>
-static int launch_eig(cudaStream_t stream, int64_t batch, int n, const double* A, double* evals, double* evecs) {
+static int launch_eig(cudaStream_t stream, int64_t batch, int n, const double* A, double* evals, double* evecs, int* info) {
   const size_t smem = eig_smem(n);
   GDFT_CUDA_TRY(cudaFuncSetAttribute(sym_eig_jacobi_kernel<NB, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sym_eig_jacobi_kernel<NB, NV><<<(unsigned)batch, EIG_THREADS, smem, stream>>>(n, A, evals, evecs);
+  sym_eig_jacobi_kernel<NB, NV><<<(unsigned)batch, EIG_THREADS, smem, stream>>>(n, A, evals, evecs, info);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
@@ -485,22 +494,36 @@ static int launch_eig(cudaStream_t stream, int64_t batch, int n, const double* A
 
 using namespace gdft;
 
-extern "C" int gdft_sym_eigh_max_n(void) { return EIG_MAX_N; }
+namespace gdft {
+int sym_eigh_cluster(cudaStream_t stream, int64_t batch, int n, const double* A, const double* V0, double* evals, double* evecs, int* info);
+int sym_eigh_cluster_max_n();
+}
 
-extern "C" int gdft_sym_eigh_warm(gdft_stream_t stream_, int64_t batch, int64_t n, const double* A, const double* V0, double* evals,
-                                  double* evecs) {
-  if (batch <= 0 || n <= 0 || n > EIG_MAX_N || batch > 65535) return GDFT_BAD_SHAPE;
+extern "C" int gdft_sym_eigh_max_n(void) { return sym_eigh_cluster_max_n(); }
+
+extern "C" int gdft_sym_eigh_ex(gdft_stream_t stream_, int64_t batch, int64_t n, const double* A, const double* V0, double* evals,
+                                double* evecs, int* info) {
+  if (batch <= 0 || n <= 0 || n > sym_eigh_cluster_max_n() || batch > 8191) return GDFT_BAD_SHAPE;
   if (!A || !evals || !evecs) return GDFT_BAD_ARGUMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   // upper blocks per A thread (256 threads): npair (npair + 1) / 2 <= 253 up to n = 44, <= 528 up to n = 64; V rows per V warp: n / 8
-  if (n <= 16) return launch_eig_small<1, 2>(stream, batch, (int)n, A, V0, evals, evecs);
-  if (n <= 32) return launch_eig_small<1, 4>(stream, batch, (int)n, A, V0, evals, evecs);
-  if (n <= 44) return launch_eig_small<1, 6>(stream, batch, (int)n, A, V0, evals, evecs);
-  if (n <= 48) return launch_eig_small<3, 6>(stream, batch, (int)n, A, V0, evals, evecs);
-  if (n <= 64) return launch_eig_small<3, 8>(stream, batch, (int)n, A, V0, evals, evecs);
-  return launch_eig<4, 8>(stream, batch, (int)n, A, evals, evecs);  // 65..90: A and V both in shared memory (cold start only)
+  if (n <= 16) return launch_eig_small<1, 2>(stream, batch, (int)n, A, V0, evals, evecs, info);
+  if (n <= 32) return launch_eig_small<1, 4>(stream, batch, (int)n, A, V0, evals, evecs, info);
+  if (n <= 44) return launch_eig_small<1, 6>(stream, batch, (int)n, A, V0, evals, evecs, info);
+  if (n <= 48) return launch_eig_small<3, 6>(stream, batch, (int)n, A, V0, evals, evecs, info);
+  if (n <= 64) return launch_eig_small<3, 8>(stream, batch, (int)n, A, V0, evals, evecs, info);
+  if (n <= EIG_MAX_N) {
+    const char* e = getenv("GDFT_EIGH_ONE_CTA");  // 65..90: the one-CTA kernel (A and V in shared memory, cold start only) on request
+    if (e && e[0] == '1') return launch_eig<4, 8>(stream, batch, (int)n, A, evals, evecs, info);
+  }
+  return sym_eigh_cluster(stream, batch, (int)n, A, V0, evals, evecs, info);  // one 8-CTA cluster per matrix (eigh_cluster.cu)
+}
+
+extern "C" int gdft_sym_eigh_warm(gdft_stream_t stream, int64_t batch, int64_t n, const double* A, const double* V0, double* evals,
+                                  double* evecs) {
+  return gdft_sym_eigh_ex(stream, batch, n, A, V0, evals, evecs, nullptr);
 }
 
 extern "C" int gdft_sym_eigh(gdft_stream_t stream, int64_t batch, int64_t n, const double* A, double* evals, double* evecs) {
-  return gdft_sym_eigh_warm(stream, batch, n, A, nullptr, evals, evecs);
+  return gdft_sym_eigh_ex(stream, batch, n, A, nullptr, evals, evecs, nullptr);
 }

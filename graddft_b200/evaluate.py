@@ -4,9 +4,10 @@
 re-stated step for step; `make_jitted_scf_loop` is the name BASELINE.json uses for `diff_scf_loop`.  Everything in
 the loop body other than `compute_energy` is n x n work (DIIS ring buffers and an 11 x 11 solve, a Cholesky-reduced
 symmetric eigenproblem per spin, aufbau occupations, rdm1 = C occ C^T) and stays in the host framework (cuSOLVER /
-cuBLAS through torch), as the reference leaves it to XLA.  Upstream quirks are kept: the
-extra "final diagonalisation" is computed and discarded, and the DIIS ring-buffer write at cycle == max_diis is
-dropped.
+cuBLAS through torch), as the reference leaves it to XLA; the eigenproblem itself is a kernel of the library up to
+n = 320 (one CTA per matrix up to n = 64, one 8-CTA cluster beyond).  Upstream quirks are kept: the
+DIIS ring-buffer write at cycle == max_diis is dropped; the extra "final diagonalisation" whose result upstream discards
+(evaluate.py:1021-1031) is skipped, nothing observable depends on it.
 """
 from __future__ import annotations
 
@@ -147,15 +148,19 @@ def safe_general_eigh(A: Array, B: Array, L_inv: Optional[Array] = None, shard=N
     if L_inv is None:
         L_inv = overlap_factor(B)
     C = L_inv @ A @ L_inv.transpose(-1, -2)
-    if (warm is not None and C.shape[-1] <= 64 and ops.sym_eigh_supported(C)
-            and not (torch.is_grad_enabled() and C.requires_grad)):
+    if (warm is not None and ops.sym_eigh_supported(C) and not (torch.is_grad_enabled() and C.requires_grad)):
         uses = warm.get("uses", 0)
-        evals, evecs_t = ops.sym_eigh(C, warm.get("V") if uses % WARM_RESTART_EVERY else None)
+        # n <= 64 returns V0 V', whose orthogonality drifts: a cold start every few cycles; the cluster kernel (n > 64)
+        # re-derives its eigenvectors from (C + sigma I) V0 every time and needs none
+        cold = C.shape[-1] <= 64 and uses % WARM_RESTART_EVERY == 0
+        evals, evecs_t = ops.sym_eigh(C, None if cold else warm.get("V"), warm.get("info"))
         warm["V"], warm["uses"] = evecs_t, uses + 1
         return evals, L_inv.transpose(-1, -2) @ evecs_t
     no_grad = not (torch.is_grad_enabled() and C.requires_grad)
-    if warm is not None and no_grad and C.is_cuda and not ops.sym_eigh_supported(C):
-        # beyond the Jacobi kernel: refine the previous cycle's eigenvectors; the full solver is the fallback
+    if warm is not None and no_grad and C.is_cuda and shard is None and not ops.sym_eigh_supported(C):
+        # beyond the library's own eigensolvers (n > 320), single GPU only (every branch below is decided from host reads
+        # of this rank's own data; ranks of a sharded molecule must not diverge, so they always take the collective solve
+        # further down): refine the previous cycle's eigenvectors; the full solver is the fallback
         # ... attempted only once the SCF has settled: the step needs a change of C well below its smallest eigenvalue
         # gaps (in the benzene-shaped loop it is accepted from cycle 9 on, 1.2 ms against 5.6 ms, and a refused attempt
         # costs 0.6 ms), so the relative change of C since the previous cycle gates it

@@ -563,10 +563,11 @@ def sym_eigh_supported(A: torch.Tensor) -> bool:
     return A.is_cuda and A.dtype == F64 and A.dim() >= 2 and A.shape[-1] == A.shape[-2] and 0 < A.shape[-1] <= lib().gdft_sym_eigh_max_n()
 
 
-def sym_eigh(A: torch.Tensor, V0: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+def sym_eigh(A: torch.Tensor, V0: Optional[torch.Tensor] = None, info: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(eigenvalues ascending [..., n], eigenvectors as columns [..., n, n]) of symmetric A[..., n, n]; no autograd
     (evaluate.safe_eigh supplies the VJP), no host synchronisation.  `V0` (same shape, ORTHOGONAL: the eigenvectors of a
-    nearby matrix) warm-starts the Jacobi sweeps."""
+    nearby matrix) warm-starts the Jacobi sweeps.  `info` (optional int32 CUDA tensor, one entry per matrix) receives the
+    sweep count, -1 if the sweep bound was hit, -2 for a non-finite result -- written stream-ordered, read it when convenient."""
     A = _c(A.detach())
     n = int(A.shape[-1])
     batch = A.numel() // (n * n)
@@ -576,8 +577,14 @@ def sym_eigh(A: torch.Tensor, V0: Optional[torch.Tensor] = None) -> Tuple[torch.
         V0 = _c(V0.detach())
         if V0.shape != A.shape:
             raise TypeError(f"V0 {tuple(V0.shape)} does not match A {tuple(A.shape)}")
+    info_p = None
+    if info is not None:
+        if info.dtype != torch.int32 or not info.is_cuda or info.numel() < batch or not info.is_contiguous():
+            raise TypeError("info must be a contiguous int32 CUDA tensor with one entry per matrix")
+        from ctypes import c_void_p
+        info_p = c_void_p(info.data_ptr())
     with _timed("gdft_sym_eigh"):
-        check(lib().gdft_sym_eigh_warm(stream_ptr(), batch, n, ptr(A), ptr(V0), ptr(evals), ptr(evecs)), "gdft_sym_eigh_warm")
+        check(lib().gdft_sym_eigh_ex(stream_ptr(), batch, n, ptr(A), ptr(V0), ptr(evals), ptr(evecs), info_p), "gdft_sym_eigh_ex")
     return evals, evecs
 
 

@@ -218,6 +218,14 @@ int gdft_sym_eigh(gdft_stream_t stream, int64_t batch, int64_t n, const double* 
  * larger n ignore V0.  The result is the eigen-decomposition of A either way; only the sweep count changes. */
 int gdft_sym_eigh_warm(gdft_stream_t stream, int64_t batch, int64_t n, const double* A, const double* V0, double* evals,
                        double* evecs);
+/* The general entry: n <= 64 one CTA per matrix (two-sided Jacobi in shared memory, above); 64 < n <= gdft_sym_eigh_max_n()
+ * (320: the benzene/def2-TZVP class) one 8-CTA thread-block cluster per matrix running one-sided (Hestenes) Jacobi on
+ * (A + sigma I) V0 with the column pairs handed round the cluster through distributed shared memory (csrc/eigh_cluster.cu);
+ * V0 warm-starts both.  A is taken as symmetric (its rows are read as columns).  `info[b]` (optional, DEVICE int per
+ * matrix, written stream-ordered: poll it lazily or assert on it in tests) receives the number of sweeps, -1 if the sweep
+ * bound was hit before convergence, -2 for a non-finite result.  No host synchronisation: capturable in a CUDA graph. */
+int gdft_sym_eigh_ex(gdft_stream_t stream, int64_t batch, int64_t n, const double* A, const double* V0, double* evals,
+                     double* evecs, int* info);
 
 /* The two reductions of the CDIIS step (grad_dft/evaluate.py:1165 "iskl,jskl->sij" and :1198 "si,isjk->sjk") over the ring
  * buffers err_vec / fock_vec [m,2,n,n]: gram[2,m,m] (symmetric, deterministic summation order) and the extrapolated

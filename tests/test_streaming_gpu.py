@@ -291,7 +291,7 @@ def test_sym_eigh_jacobi(cuda_device, n):
     assert float((V.transpose(1, 2) @ V - eye).abs().max()) < 1e-13 * max(n, 4)
     resid = (A @ V - V * w.unsqueeze(1)).abs().amax(dim=(1, 2))
     assert bool((resid <= 1e-13 * scale * max(n, 4)).all())
-    assert not ops.sym_eigh_supported(torch.zeros(2, 200, 200, dtype=F64, device=cuda_device))
+    assert not ops.sym_eigh_supported(torch.zeros(2, 400, 400, dtype=F64, device=cuda_device))
 
 
 @pytest.mark.parametrize("m,n", [(10, 43), (10, 7), (3, 64), (10, 264)])
@@ -412,3 +412,71 @@ def test_refine_eigh(cuda_device, n):
             Md = M.to(cuda_device)
             assert float((Md @ V - V * w.unsqueeze(-2)).abs().max()) < 1e-11 * float(w.abs().max())
     assert refine_eigh(B.to(cuda_device), far.to(cuda_device))[0] is None
+
+
+@pytest.mark.parametrize("n", [65, 66, 90, 96, 128, 161, 200, 264, 265, 320])
+def test_sym_eigh_cluster(cuda_device, n):
+    """Row f1 beyond n = 64 (csrc/eigh_cluster.cu: one 8-CTA cluster per matrix, one-sided Jacobi on (A + sigma I) V0) against
+    LAPACK on the CPU at 1e-12: random, diagonal, (n-1)-fold degenerate and nearly diagonal inputs; the status word; a
+    warm start from the eigenvectors of a nearby matrix, from the exact eigenvectors and from an unrelated orthogonal basis."""
+    g = torch.Generator().manual_seed(100 + n)
+    A = torch.randn(4, n, n, generator=g, dtype=F64)
+    A = 0.5 * (A + A.transpose(1, 2))
+    A[1] = torch.diag(torch.randn(n, generator=g, dtype=F64))
+    u = torch.randn(n, 1, generator=g, dtype=F64)
+    A[2] = torch.eye(n, dtype=F64) * 3.0 + u @ u.T
+    A[3] = A[3] * 1e-8 + torch.diag(torch.linspace(-50.0, 50.0, n, dtype=F64))
+    eye = torch.eye(n, dtype=F64)
+
+    def check(Ah, w, V, tol=1e-12):
+        w, V = w.cpu(), V.cpu()
+        w_ref = torch.linalg.eigvalsh(Ah)
+        rho = w_ref.abs().amax(dim=-1).clamp_min(1e-300)
+        assert bool(((w - w_ref).abs().amax(dim=-1) <= tol * rho).all()), float(((w - w_ref).abs().amax(dim=-1) / rho).max())
+        assert bool((w[..., 1:] >= w[..., :-1]).all())
+        assert float((V.transpose(-1, -2) @ V - eye).abs().max()) < tol
+        resid = (Ah @ V - V * w.unsqueeze(-2)).abs().amax(dim=(-1, -2))
+        assert bool((resid <= tol * rho).all()), float((resid / rho).max())
+
+    Ad = A.to(cuda_device)
+    assert ops.sym_eigh_supported(Ad)
+    info = torch.full((4,), -99, dtype=torch.int32, device=cuda_device)
+    w, V = ops.sym_eigh(Ad, info=info)
+    check(A, w, V)
+    cold = info.cpu()
+    assert bool((cold >= 1).all()) and bool((cold <= 20).all()), cold
+    assert int(cold[1]) == 1  # a diagonal matrix: one sweep without a single rotation
+    # warm starts
+    P = torch.randn(2, n, n, generator=g, dtype=F64)
+    A2 = A[:2] + 1e-4 * (P + P.transpose(1, 2))
+    A2[1] = A[0] + 1e-7 * (P[1] + P[1].T)
+    A2d = A2.to(cuda_device)
+    V_prev = torch.stack([V[0], V[0]])
+    info2 = torch.full((2,), -99, dtype=torch.int32, device=cuda_device)
+    w2, V2 = ops.sym_eigh(A2d, V_prev, info=info2)
+    check(A2, w2, V2)
+    assert int(info2[0]) < int(cold[0]) and int(info2[1]) <= int(info2[0]), (info2, cold)
+    w3, V3 = ops.sym_eigh(A2d, V2, info=info2)  # the exact eigenvectors: nothing to rotate
+    check(A2, w3, V3)
+    assert int(info2.max()) <= 2
+    Q, _ = torch.linalg.qr(torch.randn(2, n, n, generator=g, dtype=F64))
+    w4, V4 = ops.sym_eigh(A2d, Q.to(cuda_device), info=info2)
+    check(A2, w4, V4)
+    # a non-finite input is reported, not hidden
+    bad = Ad[:1].clone()
+    bad[0, 3, 5] = float("nan")
+    ops.sym_eigh(bad, info=info2)
+    assert int(info2[0]) == -2
+
+
+def test_sym_eigh_status_word_small(cuda_device):
+    """The one-CTA kernels report their sweep count too (ADVICE: no silent non-convergence inside a captured graph)."""
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(3, 43, 43, generator=g, dtype=F64)
+    A = (A + A.transpose(1, 2)).to(cuda_device)
+    info = torch.full((3,), -99, dtype=torch.int32, device=cuda_device)
+    ops.sym_eigh(A, info=info)
+    assert bool((info >= 1).all()) and bool((info <= 12).all()), info
+    A[1, 0, 0] = float("inf")
+    ops.sym_eigh(A, info=info)
+    assert int(info[1]) == -2 and int(info[0]) >= 1
