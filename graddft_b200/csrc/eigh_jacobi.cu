@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_kernel(int n, cons
     if (tid == 0) { double s = 0; for (int w = 0; w < EIG_THREADS / 32; w++) s += red[w]; s_tot = s; }
     __syncthreads();
     if (!(s_off > eig_tol(n) * s_tot)) {  // also leaves on NaN
-      if (tid == 0 && info != nullptr) info[blockIdx.x] = (s_off == s_off && s_tot == s_tot) ? sweep : -2;
+      if (tid == 0 && info != nullptr) info[blockIdx.x] = (s_off - s_off == 0.0 && s_tot - s_tot == 0.0) ? sweep : -2  /* inf - inf and NaN - NaN are NaN */;
       break;
     }
     if (tid == 0 && info != nullptr && sweep == EIG_MAX_SWEEPS - 1) info[blockIdx.x] = -1;  // the bound was hit
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
     if (tid == 0) { double s = 0; for (int w = 0; w < NW; w++) s += red[w]; s_tot = s; }
     __syncthreads();
     if (!(s_off > eig_tol(n) * s_tot)) {  // also leaves on NaN
-      if (tid == 0 && info != nullptr) info[blockIdx.x] = (s_off == s_off && s_tot == s_tot) ? sweep : -2;
+      if (tid == 0 && info != nullptr) info[blockIdx.x] = (s_off - s_off == 0.0 && s_tot - s_tot == 0.0) ? sweep : -2  /* inf - inf and NaN - NaN are NaN */;
       break;
     }
     if (tid == 0 && info != nullptr && sweep == EIG_MAX_SWEEPS - 1) info[blockIdx.x] = -1;  // the bound was hit

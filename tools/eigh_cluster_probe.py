@@ -39,4 +39,14 @@ for n in (65, 90, 96, 128, 160, 200, 264, 320):
         os.environ["GDFT_EIGH_ONE_CTA"] = "1"
         line += f" | one-CTA kernel {timeit(lambda: ops.sym_eigh(A)):6.3f} ms"
         os.environ["GDFT_EIGH_ONE_CTA"] = "0"
+    if n >= 128:
+        import os
+        for cl in ("8", "16"):
+            os.environ["GDFT_EIGH_CLUSTER"] = cl
+            tc = timeit(lambda: ops.sym_eigh(A, info=info))
+            P = torch.randn(2, n, n, generator=g, dtype=torch.float64).to(dev)
+            A2 = A + 1e-5 * (P + P.transpose(1, 2))
+            tw = timeit(lambda: ops.sym_eigh(A2, V, info=info))
+            line += f" | cluster {cl}: cold {tc:6.3f} warm {tw:6.3f} {info.tolist()}"
+        del os.environ["GDFT_EIGH_CLUSTER"]
     print(line, flush=True)
