@@ -15,7 +15,7 @@ import torch
 LIB_PATH = Path(__file__).resolve().parent / "libgdft_b200.so"
 
 GDFT_RHO, GDFT_GRAD, GDFT_TAU, GDFT_LAPL, GDFT_HF = 1, 2, 4, 8, 16
-OP_DENSITY_FWD, OP_DENSITY_BWD, OP_HF_FOCK, OP_ERI_J, OP_XC_INTEGRATE, OP_LN_ELU = 1, 2, 3, 4, 5, 6
+OP_DENSITY_FWD, OP_DENSITY_BWD, OP_HF_FOCK, OP_ERI_J, OP_XC_INTEGRATE, OP_LN_ELU, OP_DENSE = 1, 2, 3, 4, 5, 6, 7
 PW_IDS = {
     "LSDA_X": 0, "B88_X": 1, "VWN_C": 2, "LYP_C": 3, "PW92_C": 4, "B3LYP_SET": 5, "B88_SET": 6,
     "DM21_INPUTS": 7, "DM21_LDA": 8, "DM21_GGA": 9, "DM21_MGGA": 10, "FEAT_LDA": 11, "FEAT_GGA": 12, "FEAT_MGGA": 13,
@@ -51,6 +51,12 @@ SIGNATURES = {
     "gdft_ln_elu_bwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_dense_ln_elu_fwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, c_double, _P, _P]),
     "gdft_dense_ln_elu_bwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "gdft_dense_supported": (c_int, [c_int64, c_int64]),
+    "gdft_dense_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "gdft_dense_block_fwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, c_double, _P, _P, _P]),
+    "gdft_dense_block_bwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "gdft_dense_bwd_weight": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_size_t]),
+    "gdft_dense_block_bwd_last": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_sym_eigh_max_n": (c_int, []),
     "gdft_sym_eigh": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "gdft_sym_eigh_warm": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P]),

@@ -18,7 +18,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = CSRC / "build"
 LIB = HERE / "libgdft_b200.so"
-SOURCES = ["api.cu", "density_fwd.cu", "density_bwd.cu", "pointwise.cu", "eri_integrate.cu", "mlp_epilogue.cu", "eigh_jacobi.cu", "eigh_cluster.cu", "chi_contract.cu", "scf_glue.cu", "jax_ffi.cu"]
+SOURCES = ["api.cu", "density_fwd.cu", "density_bwd.cu", "pointwise.cu", "eri_integrate.cu", "mlp_epilogue.cu", "dense_gemm.cu", "eigh_jacobi.cu", "eigh_cluster.cu", "chi_contract.cu", "scf_glue.cu", "jax_ffi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",

@@ -43,6 +43,7 @@ size_t density_bwd_workspace(int64_t N, int64_t n, int ncoef_rows, int nout);
 size_t eri_workspace(int64_t n);
 size_t integrate_workspace(int64_t N);
 size_t ln_elu_workspace(int64_t N, int64_t W);
+size_t dense_workspace(int64_t N, int64_t K, int64_t Wd);
 
 // ---- basis packing ------------------------------------------------------------------------------
 // packed[c][r][b]: c=0 ao; c=1..3 grad_ao[r][b][c-1]; c=4 sum_i grad2_ao[r][b][i]; columns n..npad-1 zero.
@@ -134,6 +135,7 @@ extern "C" size_t gdft_workspace_bytes(int op, int64_t N, int64_t n, int flags, 
     case GDFT_OP_ERI_J: return eri_workspace(n);
     case GDFT_OP_XC_INTEGRATE: return integrate_workspace(N);
     case GDFT_OP_LN_ELU: return ln_elu_workspace(N, n);
+    case GDFT_OP_DENSE: return dense_workspace(N, n, flags);
     default: (void)flags; return 0;
   }
 }

@@ -295,6 +295,79 @@ __global__ void dense_colsum_kernel(const double* __restrict__ part, int64_t nbl
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// The LAST block of a trunk has no GEMM after it whose epilogue could undo its ELU / LayerNorm: one streaming pass, a warp
+// per row (W <= 256: 4 double2 per lane), same formulas as the LN_ELU_BWD epilogue, per-CTA column partials.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int LB_WARPS = 8, LB_MAX_CTAS = 148 * 4;
+
+__global__ void __launch_bounds__(LB_WARPS * 32, 2)
+dense_block_bwd_last_kernel(int64_t N, int W, const double* __restrict__ out_bar, const double* __restrict__ out, const double* __restrict__ xhat,
+                            const double* __restrict__ rstd, const double* __restrict__ gamma, double* __restrict__ z_bar, double* __restrict__ colpart) {
+  __shared__ double sred[LB_WARPS][3][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = W >> 1;
+  const double inv_w = 1.0 / W;
+  double2 cg[4], cb[4], cz[4], gm[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    cg[i] = cb[i] = cz[i] = make_double2(0.0, 0.0);
+    gm[i] = lane + 32 * i < nv ? reinterpret_cast<const double2*>(gamma)[lane + 32 * i] : make_double2(0.0, 0.0);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * LB_WARPS + warp; row < N; row += (int64_t)gridDim.x * LB_WARPS) {
+    const double2* ob2 = reinterpret_cast<const double2*>(out_bar + row * W);
+    const double2* o2 = reinterpret_cast<const double2*>(out + row * W);
+    const double2* x2 = reinterpret_cast<const double2*>(xhat + row * W);
+    double2 gh[4], xh[4];
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = lane + 32 * i;
+      gh[i] = xh[i] = make_double2(0.0, 0.0);
+      if (c < nv) {
+        const double2 ob = __ldcs(ob2 + c), o = __ldcs(o2 + c);
+        xh[i] = __ldcs(x2 + c);
+        const double t0 = ob.x * (o.x > 0.0 ? 1.0 : o.x + 1.0), t1 = ob.y * (o.y > 0.0 ? 1.0 : o.y + 1.0);
+        cg[i].x = fma(t0, xh[i].x, cg[i].x); cg[i].y = fma(t1, xh[i].y, cg[i].y);
+        cb[i].x += t0; cb[i].y += t1;
+        gh[i] = make_double2(t0 * gm[i].x, t1 * gm[i].y);
+        s1 += gh[i].x + gh[i].y;
+        s2 = fma(gh[i].x, xh[i].x, fma(gh[i].y, xh[i].y, s2));
+      }
+    }
+    const double m1 = warp_sum(s1) * inv_w, m2 = warp_sum(s2) * inv_w, rs = rstd[row];
+    double2* z2 = reinterpret_cast<double2*>(z_bar + row * W);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const double z0 = rs * (gh[i].x - m1 - xh[i].x * m2), z1 = rs * (gh[i].y - m1 - xh[i].y * m2);
+        z2[c] = make_double2(z0, z1);
+        cz[i].x += z0; cz[i].y += z1;
+      }
+    }
+  }
+  if (colpart == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = 2 * (lane + 32 * i);
+    if (c < W) {
+      sred[warp][0][c] = cg[i].x; sred[warp][0][c + 1] = cg[i].y;
+      sred[warp][1][c] = cb[i].x; sred[warp][1][c + 1] = cb[i].y;
+      sred[warp][2][c] = cz[i].x; sred[warp][2][c + 1] = cz[i].y;
+    }
+  }
+  __syncthreads();
+  double* cp = colpart + (size_t)blockIdx.x * 3 * W;
+  for (int idx = threadIdx.x; idx < 3 * W; idx += blockDim.x) {
+    const int q = idx / W, c = idx - q * W;
+    double s = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < LB_WARPS; w2++) s += sred[w2][q][c];
+    cp[idx] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Wbar[K, Wd] = A[N, K]^T Z[N, Wd]
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TN_TILE = 128, TN_KT = 16, TN_PITCH = TN_TILE + 4, TN_STAGES = 4, TN_THREADS = 256;
@@ -317,7 +390,7 @@ dense_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int tile = blockIdx.x % (p.tiles_m * p.tiles_n), slice = blockIdx.x / (p.tiles_m * p.tiles_n);
   const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
   const int64_t r_begin = (int64_t)slice * p.rows_per_slice;
-  const int64_t r_end = imin64(p.N, r_begin + p.rows_per_slice);
+  const int64_t r_end = (p.N < r_begin + p.rows_per_slice) ? p.N : r_begin + p.rows_per_slice;
   const int total = r_end > r_begin ? (int)((r_end - r_begin + TN_KT - 1) / TN_KT) : 0;
   if (tid == 0) {
     tma_prefetch_desc(&tmA);
@@ -351,7 +424,7 @@ dense_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (tid == 0 && it + TN_STAGES - 1 < total) issue(it + TN_STAGES - 1);
     // rows beyond r_end inside the last k-tile belong to the next slice (or are zero-filled past N): mask them
     const int64_t rbase = r_begin + (int64_t)it * TN_KT;
-    const int kvalid = (int)imin64(TN_KT, r_end - rbase);
+    const int kvalid = (r_end - rbase < TN_KT) ? (int)(r_end - rbase) : TN_KT;
     // A^T fragment: a = A_tile[k = t][m = g]; B fragment: b = Z_tile[k = t][n = g]
     const double* sA = sStage + st * STAGE_ELEMS + t * TN_PITCH + wm * 64 + g;
     const double* sZ = sStage + st * STAGE_ELEMS + TN_KT * TN_PITCH + t * TN_PITCH + wn * 32 + g;
@@ -527,5 +600,27 @@ extern "C" int gdft_dense_bwd_weight(gdft_stream_t stream_, int64_t N, int64_t K
   const int64_t count = K * Wd;
   dense_tn_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(p.partial, p.kslices, count, kernel_bar);
   GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+extern "C" int gdft_dense_block_bwd_last(gdft_stream_t stream_, int64_t N, int64_t W, const double* out_bar, const double* out, const double* xhat,
+                                         const double* rstd, const double* scale, double* z_bar, double* scale_bar, double* bias_bar,
+                                         double* dense_bias_bar, void* ws, size_t ws_bytes) {
+  if (!dense_shape_ok(N, W, W)) return GDFT_BAD_SHAPE;
+  if (!out_bar || !out || !xhat || !rstd || !scale || !z_bar) return GDFT_BAD_ARGUMENT;
+  if (!aligned16(out_bar) || !aligned16(out) || !aligned16(xhat) || !aligned16(scale) || !aligned16(z_bar) || !aligned16(ws)) return GDFT_BAD_ALIGNMENT;
+  const bool pg = scale_bar || bias_bar || dense_bias_bar;
+  int64_t ctas = (N + LB_WARPS - 1) / LB_WARPS;
+  if (ctas > LB_MAX_CTAS) ctas = LB_MAX_CTAS;
+  if (pg && ws_bytes < (size_t)ctas * 3 * W * 8) return GDFT_WORKSPACE_TOO_SMALL;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  double* colpart = pg ? static_cast<double*>(ws) : nullptr;
+  dense_block_bwd_last_kernel<<<(unsigned)ctas, LB_WARPS * 32, 0, stream>>>(N, (int)W, out_bar, out, xhat, rstd, scale, z_bar, colpart);
+  GDFT_LAUNCH_CHECK();
+  if (pg) {
+    const int cols3 = 3 * (int)W;
+    dense_colsum_kernel<<<(cols3 + 31) / 32, 256, 0, stream>>>(colpart, ctas, cols3, scale_bar, bias_bar, dense_bias_bar, (int)W);
+    GDFT_LAUNCH_CHECK();
+  }
   return GDFT_OK;
 }

@@ -190,7 +190,10 @@ class NeuralFunctional(Functional):
         i = self._dense_i
         object.__setattr__(self, "_dense_i", i + 1)
         p = self._bound
-        return x @ p[f"Dense_{i}.kernel"] + p[f"Dense_{i}.bias"]
+        kernel, bias = p[f"Dense_{i}.kernel"], p[f"Dense_{i}.bias"]
+        if ops.dense_supported(x, kernel):
+            return ops.dense_layer(x, kernel, bias)  # FP64 tensor-core GEMM of the library (gdft_dense_fwd)
+        return x @ kernel + bias  # second-order builds, CPU tensors of the tests' oracles, widths beyond the kernel
 
     def layer_norm(self, x: Array, eps: float = 1e-6) -> Array:
         i = self._ln_i
@@ -204,6 +207,8 @@ class NeuralFunctional(Functional):
         """One loop body of default_nn (grad_dft/functional.py:809-819): activation(LayerNorm(dense(x) + x)).  With the ELU
         activation inside a first-order build this is the library GEMM followed by ONE fused kernel pass
         (gdft_ln_elu_fwd / _bwd) instead of ~10 elementwise kernels; otherwise the same composite as upstream."""
+        if self.activation is torch.nn.functional.elu and ops.residual_trunk_supported(x, x.shape[-1]):
+            return self.residual_trunk(x, 1, eps)
         if self.activation is torch.nn.functional.elu and ops.residual_layernorm_elu_supported(x):
             i = self._ln_i
             object.__setattr__(self, "_ln_i", i + 1)
@@ -214,6 +219,26 @@ class NeuralFunctional(Functional):
             return ops.residual_layernorm_elu(x @ p[f"Dense_{j}.kernel"], x, p[f"LayerNorm_{i}.scale"], p[f"LayerNorm_{i}.bias"], eps,
                                               ybias=p[f"Dense_{j}.bias"])
         return self.activation(self.layer_norm(self.dense(x) + x, eps))
+
+    def residual_trunk(self, x: Array, nblocks: int, eps: float = 1e-6) -> Array:
+        """`nblocks` consecutive residual blocks (the whole loop of default_nn, functional.py:809-819).  Inside a first-order
+        build with the ELU activation and a width the GEMM kernels take, the run is one differentiable unit of library
+        kernels (ops.residual_trunk: one fused GEMM per block forward, one per block reverse); otherwise block by block."""
+        if not (self.activation is torch.nn.functional.elu and ops.residual_trunk_supported(x, x.shape[-1])):
+            for _ in range(nblocks):
+                x = self.residual_block(x, eps)
+            return x
+        p = self._bound
+        i, j = self._ln_i, self._dense_i
+        blocks = []
+        for b in range(nblocks):
+            kernel = p[f"Dense_{j + b}.kernel"]
+            if tuple(kernel.shape) != (x.shape[-1], x.shape[-1]):
+                raise ValueError("residual blocks need square Dense kernels of the input width")
+            blocks.append((kernel, p[f"Dense_{j + b}.bias"], p[f"LayerNorm_{i + b}.scale"], p[f"LayerNorm_{i + b}.bias"]))
+        object.__setattr__(self, "_ln_i", i + nblocks)
+        object.__setattr__(self, "_dense_i", j + nblocks)
+        return ops.residual_trunk(x, blocks, eps)
 
     def head(self, x: Array, local_features: int, sigmoid_scale_factor: float) -> Array:
         """grad_dft/functional.py:407-419: dense -> sigmoid(x/s) * s."""
@@ -289,8 +314,7 @@ def _dm21_default_nn(instance, rhoinputs, *_, **__):
     x = canonicalize_inputs(rhoinputs)
     x = torch.log(torch.abs(x) + instance.squash_offset)
     x = torch.tanh(instance.dense(x))
-    for _ in instance.layer_widths:
-        x = instance.residual_block(x)
+    x = instance.residual_trunk(x, len(instance.layer_widths))
     return instance.head(x, instance.local_features, instance.sigmoid_scale_factor)
 
 

@@ -557,6 +557,185 @@ def residual_layernorm_elu(y: torch.Tensor, res: torch.Tensor, scale: torch.Tens
 
 
 # ---------------------------------------------------------------------------------------------------------
+# coefficient-network Dense layers as FP64 tensor-core GEMMs of the library (row f2; csrc/dense_gemm.cu)
+# ---------------------------------------------------------------------------------------------------------
+DENSE_MAX_WIDTH = 256
+
+
+def _dense_ws(N: int, K: int, Wd: int, device) -> torch.Tensor:
+    return workspace(lib().gdft_workspace_bytes(_lib.OP_DENSE, N, K, Wd, 0), device)
+
+
+def _pad_cols(t: torch.Tensor, width: int) -> torch.Tensor:
+    if t.shape[1] == width:
+        return t
+    out = t.new_zeros((t.shape[0], width))
+    out[:, :t.shape[1]] = t
+    return out
+
+
+def _up8(k: int) -> int:
+    return (k + 7) // 8 * 8
+
+
+def _dense_fwd_raw(x: torch.Tensor, kernel_t: torch.Tensor, bias: Optional[torch.Tensor], res: Optional[torch.Tensor]) -> torch.Tensor:
+    """x[N,K] @ kernel_t[Wd,K]^T (+ bias) (+ res): shapes already legal for the kernel (K even, Wd % 8 == 0, Wd <= 256)."""
+    N, K = int(x.shape[0]), int(x.shape[1])
+    Wd = int(kernel_t.shape[0])
+    out = torch.empty((N, Wd), dtype=F64, device=x.device)
+    with _timed("gdft_dense_fwd"):
+        check(lib().gdft_dense_fwd(stream_ptr(), N, K, Wd, ptr(x), ptr(kernel_t), ptr(bias), ptr(res), ptr(out)), "gdft_dense_fwd")
+    return out
+
+
+def _dense_bwd_weight_raw(x: torch.Tensor, z_bar: torch.Tensor) -> torch.Tensor:
+    N, K, Wd = int(x.shape[0]), int(x.shape[1]), int(z_bar.shape[1])
+    out = torch.empty((K, Wd), dtype=F64, device=x.device)
+    ws = _dense_ws(N, K, Wd, x.device)
+    with _timed("gdft_dense_bwd_weight"):
+        check(lib().gdft_dense_bwd_weight(stream_ptr(), N, K, Wd, ptr(x), ptr(z_bar), ptr(out), wptr(ws), ws.numel()), "gdft_dense_bwd_weight")
+    return out
+
+
+def dense_supported(x: torch.Tensor, kernel: torch.Tensor) -> bool:
+    """Whether `x @ kernel + bias` goes through the library GEMM: a first-order build on float64 CUDA tensors, output width
+    up to 256 (after padding both widths to multiples of 8: 11 -> 16 inputs, 3 -> 8 outputs for DM21's first and last layer)."""
+    return (first_order_build.depth > 0 and x.is_cuda and x.dtype == F64 and x.dim() == 2 and kernel.dim() == 2 and x.shape[0] > 0
+            and x.shape[1] == kernel.shape[0] and _up8(kernel.shape[1]) <= DENSE_MAX_WIDTH and _up8(kernel.shape[0]) <= DENSE_MAX_WIDTH)
+
+
+class _DenseLayer(Function):
+    """flax Dense, y = x K + k (grad_dft/functional.py:803,811,414), on gdft_dense_fwd; input, kernel and bias cotangents from
+    gdft_dense_fwd (x_bar = y_bar K^T) and gdft_dense_bwd_weight (K_bar = x^T y_bar).  Widths are zero-padded to multiples of 8."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, bias):
+        x, kernel = _c(x), _c(kernel)
+        K, Wd = int(kernel.shape[0]), int(kernel.shape[1])
+        K8, W8 = _up8(K), _up8(Wd)
+        xp = _pad_cols(x, K8)
+        kp = kernel.new_zeros((K8, W8))
+        kp[:K, :Wd] = kernel
+        bp = None
+        if bias is not None:
+            bp = bias.new_zeros(W8)
+            bp[:Wd] = bias
+        out = _dense_fwd_raw(xp, kp.t().contiguous(), bp, None)
+        ctx.save_for_backward(xp, kp)
+        ctx.dims = (K, Wd, bias is not None)
+        return out if W8 == Wd else out[:, :Wd]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, y_bar):
+        xp, kp = ctx.saved_tensors
+        K, Wd, has_bias = ctx.dims
+        yb = _pad_cols(_c(y_bar), kp.shape[1])
+        need = ctx.needs_input_grad
+        x_bar = k_bar = b_bar = None
+        if need[0]:
+            x_bar = _dense_fwd_raw(yb, kp, None, None)  # y_bar K^T: the transposed right operand is K as stored
+            x_bar = x_bar if x_bar.shape[1] == K else x_bar[:, :K]
+        if need[1]:
+            k_bar = _dense_bwd_weight_raw(xp, yb)[:K, :Wd]
+        if has_bias and need[2]:
+            b_bar = y_bar.sum(dim=0)
+        return x_bar, k_bar, b_bar
+
+
+def dense_layer(x: torch.Tensor, kernel: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    return _DenseLayer.apply(x, kernel, bias)
+
+
+def residual_trunk_supported(x: torch.Tensor, width: int) -> bool:
+    return (first_order_build.depth > 0 and x.is_cuda and x.dtype == F64 and x.dim() == 2 and x.shape[0] > 0 and x.shape[1] == width
+            and width % 8 == 0 and width <= DENSE_MAX_WIDTH)
+
+
+class _ResidualTrunk(Function):
+    """A run of residual blocks x <- elu(LayerNorm(x K + k + x) * scale + bias) (the loop of DM21's default_nn,
+    grad_dft/functional.py:809-819) as ONE differentiable unit: forward = one fused GEMM kernel per block
+    (gdft_dense_block_fwd); reverse = one streaming pass for the last block's ELU/LayerNorm (gdft_dense_block_bwd_last), then
+    per block one GEMM whose epilogue undoes the previous block's ELU/LayerNorm (gdft_dense_block_bwd) and one split-K GEMM
+    for the kernel cotangent (gdft_dense_bwd_weight).  params = (kernel, dense_bias, scale, bias) per block."""
+
+    @staticmethod
+    def forward(ctx, x, eps, *params):
+        L_ = lib()
+        x = _c(x)
+        N, W = int(x.shape[0]), int(x.shape[1])
+        nb = len(params) // 4
+        params = tuple(_c(t) for t in params)
+        outs, xhats, rstds = [x], [], []
+        for l in range(nb):
+            kernel, kb, scale, bias = params[4 * l:4 * l + 4]
+            out = torch.empty_like(x)
+            xhat = torch.empty_like(x)
+            rstd = torch.empty((N,), dtype=F64, device=x.device)
+            kt = kernel.t().contiguous()
+            with _timed("gdft_dense_block_fwd"):
+                check(L_.gdft_dense_block_fwd(stream_ptr(), N, W, ptr(outs[-1]), ptr(kt), ptr(kb), ptr(scale), ptr(bias), float(eps), ptr(out),
+                                              ptr(xhat), ptr(rstd)), "gdft_dense_block_fwd")
+            outs.append(out)
+            xhats.append(xhat)
+            rstds.append(rstd)
+        ctx.nb = nb
+        ctx.save_for_backward(*outs, *xhats, *rstds, *params)
+        return outs[-1]
+
+    @staticmethod
+    @once_differentiable  # second order goes through the composite path, chosen up front by the caller
+    def backward(ctx, out_bar):
+        L_ = lib()
+        nb = ctx.nb
+        saved = ctx.saved_tensors
+        outs, xhats, rstds = saved[:nb + 1], saved[nb + 1:2 * nb + 1], saved[2 * nb + 1:3 * nb + 1]
+        params = saved[3 * nb + 1:]
+        N, W = int(outs[0].shape[0]), int(outs[0].shape[1])
+        dev = outs[0].device
+        ws = _dense_ws(N, W, W, dev)
+        grads = [None] * (4 * nb)
+
+        def pgrads(l):
+            need = ctx.needs_input_grad[2 + 4 * l:2 + 4 * l + 4]
+            kb = torch.empty((W,), dtype=F64, device=dev) if need[1] else None
+            sb = torch.empty((W,), dtype=F64, device=dev) if need[2] else None
+            bb = torch.empty((W,), dtype=F64, device=dev) if need[3] else None
+            grads[4 * l + 1], grads[4 * l + 2], grads[4 * l + 3] = kb, sb, bb
+            return kb, sb, bb
+
+        z_bar = torch.empty_like(outs[0])
+        kb, sb, bb = pgrads(nb - 1)
+        with _timed("gdft_dense_block_bwd_last"):
+            check(L_.gdft_dense_block_bwd_last(stream_ptr(), N, W, ptr(_c(out_bar)), ptr(outs[nb]), ptr(xhats[nb - 1]), ptr(rstds[nb - 1]),
+                                               ptr(params[4 * (nb - 1) + 2]), ptr(z_bar), ptr(sb), ptr(bb), ptr(kb), wptr(ws), ws.numel()),
+                  "gdft_dense_block_bwd_last")
+        for l in range(nb - 1, -1, -1):
+            kernel = params[4 * l]
+            if ctx.needs_input_grad[2 + 4 * l]:
+                grads[4 * l] = _dense_bwd_weight_raw(outs[l], z_bar)  # K_bar = x_l^T z_bar_l
+            if l == 0:
+                break
+            prev = torch.empty_like(z_bar)
+            kb, sb, bb = pgrads(l - 1)
+            with _timed("gdft_dense_block_bwd"):
+                check(L_.gdft_dense_block_bwd(stream_ptr(), N, W, ptr(z_bar), ptr(kernel), ptr(outs[l]), ptr(xhats[l - 1]), ptr(rstds[l - 1]),
+                                              ptr(params[4 * (l - 1) + 2]), ptr(prev), ptr(sb), ptr(bb), ptr(kb), wptr(ws), ws.numel()),
+                      "gdft_dense_block_bwd")
+            z_bar = prev
+        x_bar = None
+        if ctx.needs_input_grad[0]:
+            x_bar = _dense_fwd_raw(z_bar, params[0], None, z_bar)  # z_bar K_0^T + z_bar (the residual branch)
+        return (x_bar, None, *grads)
+
+
+def residual_trunk(x: torch.Tensor, blocks, eps: float = 1e-6) -> torch.Tensor:
+    """`blocks`: sequence of (kernel[W,W], dense_bias[W], scale[W], bias[W]); see _ResidualTrunk."""
+    flat = [t for blk in blocks for t in blk]
+    return _ResidualTrunk.apply(x, eps, *flat)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # SCF harness: small symmetric eigenproblem (row f1)
 # ---------------------------------------------------------------------------------------------------------
 def sym_eigh_supported(A: torch.Tensor) -> bool:

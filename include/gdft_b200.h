@@ -55,7 +55,8 @@ enum gdft_op {
   GDFT_OP_HF_FOCK = 3,
   GDFT_OP_ERI_J = 4,
   GDFT_OP_XC_INTEGRATE = 5,
-  GDFT_OP_LN_ELU = 6 /* N = rows, n = width */
+  GDFT_OP_LN_ELU = 6, /* N = rows, n = width */
+  GDFT_OP_DENSE = 7   /* N = rows, n = K, flags = Wd */
 };
 
 /* closed-form per-point feature sets (grad_dft/popular_functionals.py, grad_dft/functional.py) */
@@ -205,6 +206,41 @@ int gdft_dense_ln_elu_bwd(gdft_stream_t stream, int64_t N, int64_t W, const doub
                           const double* fwd_out /*the forward output, or NULL: elu' is then recomputed with exp*/,
                           const double* out_bar, double* z_bar, double* scale_bar, double* bias_bar,
                           double* ybias_bar, void* ws, size_t ws_bytes);
+
+/* ---- coefficient-network Dense layers as FP64 tensor-core GEMMs (csrc/dense_gemm.cu; row f2) -------------------------
+ * flax Dense (x K + k) of DM21's default_nn and its residual blocks, grad_dft/functional.py:793-822, with the elementwise
+ * tail of the block fused into the GEMM epilogue.  Shapes: K even, Wd a multiple of 8 and <= 256 (gdft_dense_supported).
+ * `kernel_t` is the TRANSPOSED Dense kernel [Wd, K] (so that both operands stream with the same tile layout).
+ *   gdft_dense_fwd        out[N,Wd] = x[N,K] kernel (+ bias[Wd]) (+ res[N,Wd]).  Also the input cotangent of a Dense layer:
+ *                         x_bar = y_bar kernel^T is gdft_dense_fwd(y_bar, kernel_t := kernel as stored, ...).
+ *   gdft_dense_block_fwd  one residual block, out = elu(LayerNorm(x kernel + dense_bias + x) * scale + bias) over rows of width
+ *                         W (flax LayerNorm: biased variance, eps inside the root); also writes xhat[N,W] (the normalised
+ *                         rows) and rstd[N] for the reverse pass.
+ *   gdft_dense_block_bwd  reverse pass across the boundary between two consecutive blocks: from z_bar[N,W] (cotangent of
+ *                         z = x kernel + dense_bias + x of THIS block, whose kernel [W,W] is passed as stored) it forms the
+ *                         cotangent of this block's input, x_bar = z_bar kernel^T + z_bar -- the PREVIOUS block's output
+ *                         cotangent -- and undoes the previous block's ELU and LayerNorm in the epilogue: prev_z_bar[N,W],
+ *                         and the previous block's parameter cotangents prev_scale_bar / prev_bias_bar (LayerNorm) and
+ *                         prev_dense_bias_bar (= column sums of prev_z_bar), each [W] or NULL.  ws >= ceil(N/32)*3*W*8 bytes.
+ *   gdft_dense_bwd_weight kernel_bar[K,Wd] = x[N,K]^T z_bar[N,Wd] (split-K over the rows, deterministic); K a multiple of 8;
+ *                         ws >= 148*K*Wd*8 bytes.                                                                        */
+int gdft_dense_supported(int64_t K, int64_t Wd);
+int gdft_dense_fwd(gdft_stream_t stream, int64_t N, int64_t K, int64_t Wd, const double* x, const double* kernel_t,
+                   const double* bias, const double* res, double* out);
+int gdft_dense_block_fwd(gdft_stream_t stream, int64_t N, int64_t W, const double* x, const double* kernel_t,
+                         const double* dense_bias, const double* scale, const double* bias, double eps, double* out,
+                         double* xhat, double* rstd);
+int gdft_dense_block_bwd(gdft_stream_t stream, int64_t N, int64_t W, const double* z_bar, const double* kernel,
+                         const double* prev_out, const double* prev_xhat, const double* prev_rstd, const double* prev_scale,
+                         double* prev_z_bar, double* prev_scale_bar, double* prev_bias_bar, double* prev_dense_bias_bar,
+                         void* ws, size_t ws_bytes);
+int gdft_dense_bwd_weight(gdft_stream_t stream, int64_t N, int64_t K, int64_t Wd, const double* x, const double* z_bar,
+                          double* kernel_bar, void* ws, size_t ws_bytes);
+/* The last block of a trunk (no GEMM follows whose epilogue could undo its ELU / LayerNorm): z_bar[N,W] and the block's
+ * parameter cotangents from out_bar, in one streaming pass over (out_bar, out, xhat).  ws >= 592*3*W*8 bytes. */
+int gdft_dense_block_bwd_last(gdft_stream_t stream, int64_t N, int64_t W, const double* out_bar, const double* out,
+                              const double* xhat, const double* rstd, const double* scale, double* z_bar, double* scale_bar,
+                              double* bias_bar, double* dense_bias_bar, void* ws, size_t ws_bytes);
 
 /* ---- SCF harness: small symmetric eigenproblem -------------------------
  * evals[b, n] ascending and evecs[b, n, n] (columns) of the symmetric matrices A[b, n, n], n <= gdft_sym_eigh_max_n():
