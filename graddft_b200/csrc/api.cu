@@ -31,9 +31,16 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    // a host thread that has not touched the runtime yet (the autograd engine's worker calling an entry point whose first
+    // CUDA call is this driver function): bind the device's primary context to it and try again
+    (void)cudaFree(nullptr);
+  }
   if (r != CUDA_SUCCESS) { g_last_cuda_error = 100000 + (int)r; return GDFT_CUDA_ERROR; }
   return GDFT_OK;
 }

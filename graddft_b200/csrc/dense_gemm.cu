@@ -20,6 +20,7 @@
 //   dense_tn_kernel            Wbar[K, Wd] = A[N, K]^T Z[N, Wd]: split-K over the rows (one K-slice and one 128 x 128 output
 //     tile per CTA, 148 CTAs), operands as [16 rows][132] tiles (pitch = 4 mod 16: conflict-free transposed fragments, the
 //     4 padding columns fetched by the same TMA box), fixed-order second-stage reduce (bitwise reproducible).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gdft {
@@ -35,7 +36,33 @@ struct DenseParams {
   double *out, *xhat, *rstd, *colpart;
 };
 
-__device__ __forceinline__ double dg_elu(double o) { return o > 0.0 ? o : expm1(o); }
+// elu(o) = o > 0 ? o : expm1(o).  The library expm1 is ~45 FP64 instructions on the pipe the DMMAs of the co-resident CTA
+// use (as a separate pass, K7's forward sat at 36 % of the FP64 pipe for it); for o <= 0 this one is 19: o = k ln2 + r with
+// |r| <= ln2 / 2, exp(r) = 1 + r q(r) (Taylor to r^13 / 13!: remainder 0.3466^14 / 14! = 4e-18), s = 2^k, and
+// expm1(o) = (s - 1) + (s r) q(r) -- exact in the leading term, full relative accuracy near 0 (k = 0: s - 1 = 0), no branch.
+__device__ __forceinline__ double dg_expm1_neg(double o) {
+  o = fmax(o, -64.0);  // exp(-64) = 1.6e-28: expm1 = -1 to the last bit from -37.4 down
+  const double kf = rint(o * 1.4426950408889634);
+  double r = fma(kf, -6.93147180369123816490e-01, o);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double q = 1.6059043836821613e-10;  // 1/13!
+  q = fma(q, r, 2.08767569878681e-09);
+  q = fma(q, r, 2.505210838544172e-08);
+  q = fma(q, r, 2.755731922398589e-07);
+  q = fma(q, r, 2.7557319223985893e-06);
+  q = fma(q, r, 2.48015873015873e-05);
+  q = fma(q, r, 1.984126984126984e-04);
+  q = fma(q, r, 1.388888888888889e-03);
+  q = fma(q, r, 8.333333333333333e-03);
+  q = fma(q, r, 4.1666666666666664e-02);
+  q = fma(q, r, 1.6666666666666666e-01);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  const double sc = __longlong_as_double((long long)((int)kf + 1023) << 52);
+  return fma(sc * r, q, sc - 1.0);
+}
+__device__ __forceinline__ double dg_elu(double o) { return o > 0.0 ? o : dg_expm1_neg(o); }
+__device__ __forceinline__ void dg_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int NJ, int EPI>
 __global__ void __launch_bounds__(DG_THREADS, 2)
@@ -68,6 +95,16 @@ dense_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
   if (tid == 0)
     for (int it = 0; it < STAGES - 1 && it < total; it++) issue(it);
+  if (EPI == DG_LN_ELU_BWD) {
+    // the epilogue reads this CTA's rows of xhat_prev and out_prev (64 KB each at W = 256) straight from HBM: start them
+    // towards L2 now, under the main loop (issued at the point of use they cost the reverse GEMM 1.6 ms on top of 1.95)
+    const int lines = (int)(((size_t)BM * p.Wd * 8) / 128);
+    const int64_t nrows = p.N - row0 < BM ? p.N - row0 : BM;
+    const int live = (int)(((size_t)nrows * p.Wd * 8) / 128);
+    const char* a = reinterpret_cast<const char*>(p.xhat_prev + row0 * p.Wd);
+    const char* b = reinterpret_cast<const char*>(p.out_prev + row0 * p.Wd);
+    for (int l = tid; l < lines && l < live; l += DG_THREADS) { dg_prefetch_l2(a + (size_t)l * 128); dg_prefetch_l2(b + (size_t)l * 128); }
+  }
 
   double acc[MT][NJ][2];
 #pragma unroll
@@ -207,7 +244,6 @@ dense_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
     for (int j = 0; j < NJ; j++) gm[j] = cv[j] ? *reinterpret_cast<const double2*>(p.gamma + cbase + 8 * j) : make_double2(0.0, 0.0);
     double s1[MT], s2[MT];
-    double2 xh[MT][NJ];
     double2 cg[NJ], cb[NJ], cz[NJ];  // this thread's column sums over its MT rows
 #pragma unroll
     for (int j = 0; j < NJ; j++) cg[j] = cb[j] = cz[j] = make_double2(0.0, 0.0);
@@ -216,24 +252,27 @@ dense_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int64_t row = row0 + 8 * i + g;
       const bool rv = row < p.N;
       s1[i] = s2[i] = 0.0;
+      double2 xh[NJ], o[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
-        xh[i][j] = make_double2(0.0, 0.0);
-        double2 o = make_double2(0.0, 0.0);
+        xh[j] = o[j] = make_double2(0.0, 0.0);
         if (rv && cv[j]) {
-          xh[i][j] = __ldg(reinterpret_cast<const double2*>(p.xhat_prev + row * Wd + cbase + 8 * j));
-          o = __ldg(reinterpret_cast<const double2*>(p.out_prev + row * Wd + cbase + 8 * j));
+          xh[j] = __ldg(reinterpret_cast<const double2*>(p.xhat_prev + row * Wd + cbase + 8 * j));
+          o[j] = __ldg(reinterpret_cast<const double2*>(p.out_prev + row * Wd + cbase + 8 * j));
         } else {
           acc[i][j][0] = acc[i][j][1] = 0.0;
         }
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; j++) {
         // elu'(o) from the forward output: out > 0 <=> o > 0, else exp(o) = out + 1
-        const double t0 = acc[i][j][0] * (o.x > 0.0 ? 1.0 : o.x + 1.0), t1 = acc[i][j][1] * (o.y > 0.0 ? 1.0 : o.y + 1.0);
-        cg[j].x = fma(t0, xh[i][j].x, cg[j].x); cg[j].y = fma(t1, xh[i][j].y, cg[j].y);
+        const double t0 = acc[i][j][0] * (o[j].x > 0.0 ? 1.0 : o[j].x + 1.0), t1 = acc[i][j][1] * (o[j].y > 0.0 ? 1.0 : o[j].y + 1.0);
+        cg[j].x = fma(t0, xh[j].x, cg[j].x); cg[j].y = fma(t1, xh[j].y, cg[j].y);
         cb[j].x += t0; cb[j].y += t1;
         acc[i][j][0] = t0 * gm[j].x;
         acc[i][j][1] = t1 * gm[j].y;
         s1[i] += acc[i][j][0] + acc[i][j][1];
-        s2[i] = fma(acc[i][j][0], xh[i][j].x, fma(acc[i][j][1], xh[i][j].y, s2[i]));
+        s2[i] = fma(acc[i][j][0], xh[j].x, fma(acc[i][j][1], xh[j].y, s2[i]));
       }
     }
     row_reduce(s1, 0);
@@ -243,10 +282,14 @@ dense_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int64_t row = row0 + 8 * i + g;
       if (row < p.N) {
         const double rstd = p.rstd_prev[row], m1 = s1[i] * inv_w, m2 = s2[i] * inv_w;
+        double2 xh[NJ];  // second read of xhat (just loaded: L1 / L2) instead of 64 registers held across the reduction
+#pragma unroll
+        for (int j = 0; j < NJ; j++)
+          xh[j] = cv[j] ? __ldg(reinterpret_cast<const double2*>(p.xhat_prev + row * Wd + cbase + 8 * j)) : make_double2(0.0, 0.0);
 #pragma unroll
         for (int j = 0; j < NJ; j++) {
           if (cv[j]) {
-            const double z0 = rstd * (acc[i][j][0] - m1 - xh[i][j].x * m2), z1 = rstd * (acc[i][j][1] - m1 - xh[i][j].y * m2);
+            const double z0 = rstd * (acc[i][j][0] - m1 - xh[j].x * m2), z1 = rstd * (acc[i][j][1] - m1 - xh[j].y * m2);
             *reinterpret_cast<double2*>(p.out + row * Wd + cbase + 8 * j) = make_double2(z0, z1);
             cz[j].x += z0; cz[j].y += z1;
           }
@@ -469,7 +512,8 @@ __global__ void dense_tn_reduce_kernel(const double* __restrict__ partial, int k
 
 template <int NJ, int EPI>
 static int launch_dense_nn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const DenseParams& p) {
-  const size_t smem = (size_t)DG_STAGES * (DG_BM + 64 * NJ) * DG_BK * 8 + DG_STAGES * 8;
+  size_t smem = (size_t)DG_STAGES * (DG_BM + 64 * NJ) * DG_BK * 8 + DG_STAGES * 8;
+  if (const char* e = getenv("GDFT_DENSE_ONE_CTA")) { if (e[0] == '1' && smem < 120 * 1024) smem = 120 * 1024; }  // tuning probe: one CTA per SM
   GDFT_CUDA_TRY((cudaFuncSetAttribute(dense_nn_kernel<NJ, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   const unsigned grid = (unsigned)((p.N + DG_BM - 1) / DG_BM);
   dense_nn_kernel<NJ, EPI><<<grid, DG_THREADS, smem, stream>>>(tmA, tmB, p);

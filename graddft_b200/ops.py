@@ -560,6 +560,13 @@ def residual_layernorm_elu(y: torch.Tensor, res: torch.Tensor, scale: torch.Tens
 # coefficient-network Dense layers as FP64 tensor-core GEMMs of the library (row f2; csrc/dense_gemm.cu)
 # ---------------------------------------------------------------------------------------------------------
 DENSE_MAX_WIDTH = 256
+# Reverse pass of a trunk, per block boundary: False = the plain GEMM (x_bar = z_bar K^T + z_bar, at cuBLAS parity: 2.00 ms
+# at N = 5e5, W = 256) followed by the streaming ELU/LayerNorm reverse of the previous block (0.86 ms, 4.75 TB/s); True = ONE
+# GEMM whose epilogue does that reverse (gdft_dense_block_bwd).  The fused form saves 3 GB of HBM traffic per block but
+# measures 3.19 ms against 2.86: its epilogue is a chain of dependent global loads on a CTA that holds 128 registers of
+# accumulators, and the co-resident CTA alone cannot keep the tensor pipe full meanwhile (ncu: tensor pipe 91 % active in
+# the plain kernel, 64 % in the fused one).  Kept selectable (and tested); the forward fusion wins (2.51 vs 2.61 ms) and is used.
+DENSE_BWD_CHAIN = False
 
 
 def _dense_ws(N: int, K: int, Wd: int, device) -> torch.Tensor:
@@ -718,10 +725,17 @@ class _ResidualTrunk(Function):
                 break
             prev = torch.empty_like(z_bar)
             kb, sb, bb = pgrads(l - 1)
-            with _timed("gdft_dense_block_bwd"):
-                check(L_.gdft_dense_block_bwd(stream_ptr(), N, W, ptr(z_bar), ptr(kernel), ptr(outs[l]), ptr(xhats[l - 1]), ptr(rstds[l - 1]),
-                                              ptr(params[4 * (l - 1) + 2]), ptr(prev), ptr(sb), ptr(bb), ptr(kb), wptr(ws), ws.numel()),
-                      "gdft_dense_block_bwd")
+            if DENSE_BWD_CHAIN:
+                with _timed("gdft_dense_block_bwd"):
+                    check(L_.gdft_dense_block_bwd(stream_ptr(), N, W, ptr(z_bar), ptr(kernel), ptr(outs[l]), ptr(xhats[l - 1]), ptr(rstds[l - 1]),
+                                                  ptr(params[4 * (l - 1) + 2]), ptr(prev), ptr(sb), ptr(bb), ptr(kb), wptr(ws), ws.numel()),
+                          "gdft_dense_block_bwd")
+            else:
+                x_bar_l = _dense_fwd_raw(z_bar, kernel, None, z_bar)  # cotangent of block l-1's output: z_bar K^T + z_bar
+                with _timed("gdft_dense_block_bwd_last"):
+                    check(L_.gdft_dense_block_bwd_last(stream_ptr(), N, W, ptr(x_bar_l), ptr(outs[l]), ptr(xhats[l - 1]), ptr(rstds[l - 1]),
+                                                       ptr(params[4 * (l - 1) + 2]), ptr(prev), ptr(sb), ptr(bb), ptr(kb), wptr(ws), ws.numel()),
+                          "gdft_dense_block_bwd_last")
             z_bar = prev
         x_bar = None
         if ctx.needs_input_grad[0]:

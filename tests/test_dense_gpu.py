@@ -44,8 +44,10 @@ def test_dense_layer(cuda_device, N, K, Wd):
     assert not ops.dense_supported(x, kernel)
 
 
+@pytest.mark.parametrize("chain", [False, True])  # reverse pass: plain GEMM + streaming reverse | one GEMM with the reverse in its epilogue
 @pytest.mark.parametrize("N,W,nb", [(1000, 256, 3), (37, 8, 2), (2048, 64, 1), (513, 200, 2), (31, 256, 6), (1, 16, 1)])
-def test_residual_trunk(cuda_device, N, W, nb):
+def test_residual_trunk(cuda_device, N, W, nb, chain, monkeypatch):
+    monkeypatch.setattr(ops, "DENSE_BWD_CHAIN", chain)
     g = torch.Generator().manual_seed(N + W + nb)
     rn = lambda *s: torch.randn(*s, generator=g, dtype=F64)  # noqa: E731
     x = rn(N, W).to(cuda_device).requires_grad_(True)
