@@ -10,6 +10,7 @@ it is flax code.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Sequence
 
@@ -320,8 +321,8 @@ def _dm21_default_nn(instance, rhoinputs, *_, **__):
 
 @dataclass
 class DM21(NeuralFunctional):
-    """grad_dft/functional.py:761-928 (architecture and feature wiring; the TF-checkpoint importer is out of
-    scope -- TensorFlow is absent -- so weights come from `generate_DM21_weights`' seeded stand-in)."""
+    """grad_dft/functional.py:761-928: architecture, feature wiring and `generate_DM21_weights` (the published weights
+    read from the TF checkpoint bundle without TensorFlow, or seeded initial values)."""
 
     coefficients: Callable = _dm21_default_nn
     energy_densities: Callable = dm21_densities
@@ -345,10 +346,17 @@ class DM21(NeuralFunctional):
     def default_nn(self, rhoinputs, *a, **k):
         return _dm21_default_nn(self, rhoinputs)
 
-    def generate_DM21_weights(self, n_input_features: int = 11, seed: int = 1984, device=None) -> Dict[str, Array]:
-        """Seeded stand-in for the DeepMind checkpoint (grad_dft/functional.py:824-928 reads a TF SavedModel,
-        which needs TensorFlow): He-normal kernels, zero biases, identity added to the square residual kernels
-        (functional.py:913-921), LayerNorm scale 1 / bias 0."""
+    def generate_DM21_weights(self, folder: Optional[str] = None, num_layers_with_dm_parameters: int = 7, n_input_features: int = 11,
+                              seed: int = 1984, device=None) -> Dict[str, Array]:
+        """grad_dft/functional.py:824-928.  With `folder` (e.g. "models/DM21_model" of a Grad DFT checkout, or one of the
+        DeepMind `checkpoints/DM21*` folders) the weights of the published DM21 network are read straight from the TF
+        checkpoint bundle (`tf_bundle.load_variables`; upstream goes through `tf.saved_model.load`, which needs TensorFlow)
+        and merged into freshly initialised parameters by upstream's rule: a layer takes the checkpoint's arrays when its
+        index is <= `num_layers_with_dm_parameters` and every shape agrees, else it keeps its initial values (plus the
+        identity for square Dense kernels, functional.py:913-921).  Variable -> parameter naming as in upstream's
+        `vars_to_params` (functional.py:861-893): SquashUnprocessedData -> Dense_0, ResidualBlock[_k] -> Dense_{k+1} and
+        LayerNorm_k, OutputLayer -> Dense_7.  The checkpoint is float32; values are widened to float64 exactly.
+        Without `folder`: seeded initial values only (He-normal kernels, zero biases, LayerNorm scale 1 / bias 0)."""
         g = torch.Generator().manual_seed(seed)
         widths = list(self.layer_widths)
         p: Dict[str, Array] = {}
@@ -358,12 +366,59 @@ class DM21(NeuralFunctional):
 
         p["Dense_0.kernel"], p["Dense_0.bias"] = he(n_input_features, widths[0]), torch.zeros(widths[0], dtype=F64)
         for k, wdt in enumerate(widths):
-            p[f"Dense_{k + 1}.kernel"] = he(wdt, wdt) + torch.eye(wdt, dtype=F64)
+            p[f"Dense_{k + 1}.kernel"] = he(wdt, wdt)
             p[f"Dense_{k + 1}.bias"] = torch.zeros(wdt, dtype=F64)
             p[f"LayerNorm_{k}.scale"] = torch.ones(wdt, dtype=F64)
             p[f"LayerNorm_{k}.bias"] = torch.zeros(wdt, dtype=F64)
         p[f"Dense_{len(widths) + 1}.kernel"] = he(widths[-1], self.local_features)
         p[f"Dense_{len(widths) + 1}.bias"] = torch.zeros(self.local_features, dtype=F64)
+
+        dm = dm21_checkpoint_params(folder) if folder is not None else {}
+        modules = sorted({k.split(".")[0] for k in p})
+        for mod in modules:
+            leaves = [k for k in p if k.split(".")[0] == mod]
+            same = all(k in dm and tuple(dm[k].shape) == tuple(p[k].shape) for k in leaves)
+            if int(mod.split("_")[1]) > num_layers_with_dm_parameters or not same:
+                kern = p.get(f"{mod}.kernel")
+                if mod.startswith("Dense") and kern.shape[0] == kern.shape[1]:
+                    p[f"{mod}.kernel"] = kern + torch.eye(kern.shape[0], dtype=F64)
+            else:
+                for k in leaves:
+                    p[k] = dm[k]
         if device is not None:
             p = {k: v.to(device) for k, v in p.items()}
         return p
+
+
+def dm21_checkpoint_params(folder: str) -> Dict[str, Array]:
+    """The variables of a DM21 TF checkpoint under the flax-style names of grad_dft/functional.py:861-893."""
+    import re
+
+    from . import tf_bundle
+
+    if not os.path.isabs(folder) and not os.path.isdir(folder):
+        raise FileNotFoundError(f"DM21 checkpoint folder {folder!r} not found")
+    out: Dict[str, Array] = {}
+    for name, arr in tf_bundle.load_variables(folder).items():
+        if "ResidualBlock_" in name:
+            number = int(re.findall("ResidualBlock_[0-9]", name)[0][-1]) + 1
+        elif "ResidualBlock/" in name:
+            number = 1
+        elif "Squash" in name:
+            number = 0
+        elif "Output" in name:
+            number = 7
+        else:
+            raise ValueError(f"Unknown variable name {name!r}.")
+        t = torch.from_numpy(arr.astype("float64"))
+        if "/linear/" in name:
+            if name.endswith("/w"):
+                out[f"Dense_{number}.kernel"] = t
+            elif name.endswith("/b"):
+                out[f"Dense_{number}.bias"] = t
+        elif "/layer_norm/" in name:
+            if name.endswith("gamma"):
+                out[f"LayerNorm_{number - 1}.scale"] = t
+            elif name.endswith("beta"):
+                out[f"LayerNorm_{number - 1}.bias"] = t
+    return out
