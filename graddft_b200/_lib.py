@@ -73,7 +73,7 @@ SIGNATURES = {
     "gdft_xla_dims_size": (c_size_t, []),
 }
 # XLA custom-call adapters: void(stream, void** buffers, const char* opaque, size_t opaque_len)
-for _name in ("density_fwd", "density_bwd", "hf_fock", "eri_j", "eri_j_transpose", "xc_integrate_fwd", "xc_integrate_bwd",
+for _name in ("pack_basis", "pack_chi", "density_fwd", "density_bwd", "hf_fock", "eri_j", "eri_j_transpose", "xc_integrate_fwd", "xc_integrate_bwd",
               "pointwise_fwd", "pointwise_bwd", "pointwise_bwd2", "eri_j_rows", "eri_j_transpose_rows", "ln_elu_fwd", "ln_elu_bwd",
             "dense_ln_elu_fwd", "dense_ln_elu_bwd", "sym_eigh", "chi_contract", "diis_gram", "diis_combine"):
     SIGNATURES[f"gdft_{_name}_xla"] = (None, [_P, ctypes.POINTER(_P), c_char_p, c_size_t])

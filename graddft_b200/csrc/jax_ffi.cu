@@ -6,8 +6,9 @@
 // failing call poisons its first result with NaN (visible downstream) and records the status for
 // gdft_xla_last_status().  Nothing here contains arithmetic.
 //
-// NOTE: JAX is not installed in the build/test environment of this repository, so these adapters are compiled and
-// exported but not exercised by the test-suite; the torch bindings (ops.py) drive the very same C-ABI entry points.
+// NOTE: JAX is not installed in the build/test environment of this repository; every adapter is exercised through
+// ctypes with hand-packed buffer lists exactly as XLA's thunk would pass them (tests/test_xla_adapters_gpu.py), driven
+// by the same call plans graddft_b200/jax_ffi.py hands to jax.ffi.ffi_call.
 #include "common.cuh"
 
 namespace gdft {
@@ -36,6 +37,21 @@ using namespace gdft;
 extern "C" int gdft_xla_last_status(void) { return g_xla_status; }
 extern "C" size_t gdft_xla_dims_size(void) { return sizeof(XlaDims); }
 
+// operands: ao, grad_ao, grad2_ao (flags bit 0: grad_ao present, bit 1: grad2_ao present) | results: packed[nplanes, N, npad]
+extern "C" void gdft_pack_basis_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_pack_basis(s, d.N, d.n, (const double*)b[0], (d.flags & 1) ? (const double*)b[1] : nullptr,
+                           (d.flags & 2) ? (const double*)b[2] : nullptr, (double*)b[3], d.nplanes);
+  finish(rc, (cudaStream_t)s, b[3]);
+}
+// operands: chi[N, W, 2, n] | results: chi_packed[W, 2, N, npad]
+extern "C" void gdft_pack_chi_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_pack_chi(s, d.N, d.n, d.W, (const double*)b[0], (double*)b[1]);
+  finish(rc, (cudaStream_t)s, b[1]);
+}
 // operands: packed, rdm1, chi_packed | results: rho, grad_rho, tau, lapl, ehf, ws   (unused ones are 1-element dummies)
 extern "C" void gdft_density_fwd_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
   XlaDims d;

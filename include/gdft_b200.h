@@ -304,6 +304,8 @@ int gdft_fock_add_sym(gdft_stream_t stream, int64_t n, const double* V /*[2,n,n]
  * the entry points above and contain no arithmetic. */
 int gdft_xla_last_status(void);
 size_t gdft_xla_dims_size(void);
+void gdft_pack_basis_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_pack_chi_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_density_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_density_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_hf_fock_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);

@@ -242,3 +242,122 @@ def test_adapter_error_paths(cuda_device, mol):
     torch.cuda.synchronize()
     assert L.gdft_xla_last_status() == 5 and float(J.abs().max()) == 0.0
     jax_ffi.check_layout()
+
+
+def test_every_call_plan_of_the_jax_binding(cuda_device, mol):
+    """graddft_b200/jax_ffi.py hands `jax.ffi.ffi_call` a Plan (target, result shapes, opaque dims) per adapter.  The very
+    same plans executed here through ctypes (`run_plan_torch`) must reproduce the direct entry points bit for bit: that pins
+    operand order, result shapes, flag packing and workspace sizes of every JAX wrapper without JAX."""
+    m, basis = mol
+    dev = cuda_device
+    J = jax_ffi
+    run = J.run_plan_torch
+    N, n, W = basis.N, basis.n, basis.W
+    d1 = dummy(dev)
+    g = torch.Generator(device=dev).manual_seed(23)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=F64, device=dev)  # noqa: E731
+    covered = set()
+
+    def go(plan, ops_):
+        covered.add(plan.target)
+        out = run(plan, ops_)
+        torch.cuda.synchronize()
+        return out
+
+    (planes,) = go(J.plan_pack_basis(N, n, True, True), [m["ao"], m["grad_ao"], m["grad_n_ao2"]])
+    assert torch.equal(planes, basis.planes)
+    (chi_packed,) = go(J.plan_pack_chi(N, n, W), [m["chi"]])
+    assert torch.equal(chi_packed, basis.chi_packed)
+    flags = GDFT_RHO | GDFT_GRAD | GDFT_TAU | GDFT_LAPL | GDFT_HF
+    ref = ops._density_fwd_raw(basis, m["rdm1"], flags)
+    outs = go(J.plan_density_fwd(N, n, basis.nplanes, flags, W), [planes, m["rdm1"], chi_packed])
+    assert all(torch.equal(a, b) for a, b in zip(outs[:5], ref))
+    outs = go(J.plan_density_fwd(N, n, basis.nplanes, GDFT_RHO, W), [planes, m["rdm1"], d1])
+    assert torch.equal(outs[0], ref[0]) and outs[1].numel() == 1
+    fb = GDFT_RHO | GDFT_GRAD | GDFT_TAU | GDFT_LAPL
+    cot = [rn(*t.shape) for t in ref[:4]]
+    assert torch.equal(go(J.plan_density_bwd(N, n, basis.nplanes, fb), [planes] + cot)[0], ops._density_bwd_raw(basis, fb, *cot))
+    assert torch.equal(go(J.plan_density_bwd(N, n, basis.nplanes, GDFT_GRAD), [planes, d1, cot[1], d1, d1])[0],
+                       ops._density_bwd_raw(basis, GDFT_GRAD, None, cot[1], None, None))
+    gg = rn(W, 2, N)
+    assert torch.equal(go(J.plan_hf_fock(N, n, basis.nplanes, W), [planes, chi_packed, gg])[0], ops._hf_fock_raw(basis, gg))
+
+    P, eri = m["rdm1"].sum(0).contiguous(), m["rep_tensor"].contiguous()
+    Jref, EJref = ops._eri_j_raw(P, eri, want_energy=True)
+    Jm, EJ = go(J.plan_eri_j(n), [eri, P])
+    assert torch.equal(Jm, Jref) and torch.equal(EJ, EJref)
+    Jbar = rn(n, n)
+    assert torch.equal(go(J.plan_eri_j_transpose(n), [eri, Jbar])[0], ops._eri_jt_raw(Jbar, eri))
+    rows = 61
+    block = eri.reshape(n * n, n, n)[17:17 + rows].contiguous()
+    assert torch.equal(go(J.plan_eri_j_rows(n, rows), [block, P])[0], Jref.reshape(-1)[17:17 + rows])
+    Jb = rn(rows)
+    assert torch.equal(go(J.plan_eri_j_transpose_rows(n, rows), [block, Jb])[0], ops._CoulombJRowsT.apply(Jb, block))
+
+    rho, grho, tau, lapl = ref[:4]
+    for name, args in (("B3LYP_SET", (rho, grho, None, lapl)), ("DM21_INPUTS", (rho, grho, tau, None)), ("FEAT_MGGA", (rho, grho, tau, None))):
+        has = (args[1] is not None, args[2] is not None, args[3] is not None)
+        opnds = [a if a is not None else d1 for a in args]
+        want = ops.pointwise(name, *args)
+        (out,) = go(J.plan_pointwise_fwd(name, N, *has), opnds)
+        assert torch.equal(out, want), name
+        ob = rn(*want.shape)
+        refb = ops._PointwiseVJP.apply(_lib.PW_IDS[name], 1e-30, *args, ob)
+        res = go(J.plan_pointwise_bwd(name, N, *has), opnds + [ob])
+        assert all(torch.equal(a, b) for a, b in zip(res, refb) if b is not None), name
+        us = [rn(*t.shape) if t is not None else None for t in refb]
+        ref2 = [torch.empty_like(ob)] + [torch.empty_like(t) if t is not None else None for t in args]
+        assert _lib.lib().gdft_pointwise_bwd2(_lib.stream_ptr(), N, _lib.PW_IDS[name], 1e-30, *[_lib.ptr(a) for a in args], _lib.ptr(ob),
+                                              *[_lib.ptr(u) for u in us], *[_lib.ptr(t) for t in ref2]) == 0
+        res2 = go(J.plan_pointwise_bwd2(name, N, *has), opnds + [ob] + [u if u is not None else d1 for u in us])
+        assert all(torch.equal(a, b) for a, b in zip(res2, ref2) if b is not None), name
+
+    F = 4
+    d, w = rn(N, F), m["weights"].contiguous()
+    for c_rows in (1, N):
+        c = rn(c_rows, F)
+        cl, dl = c.clone().requires_grad_(True), d.clone().requires_grad_(True)
+        E_ref = ops.xc_integrate(cl, dl, w)
+        assert torch.equal(go(J.plan_xc_integrate_fwd(N, F, c_rows), [c, d, w])[0][0], E_ref.detach())
+        cb_ref, db_ref = torch.autograd.grad(E_ref, (cl, dl), torch.tensor(0.7, dtype=F64, device=dev))
+        cb, db, _ = go(J.plan_xc_integrate_bwd(N, F, c_rows), [c, d, w, torch.tensor([0.7], dtype=F64, device=dev)])
+        assert torch.equal(cb, cb_ref) and torch.equal(db, db_ref)
+
+    Nn, Wd = 301, 64
+    L = _lib.lib()
+    y, res_, scale, bias, ybias, ob = rn(Nn, Wd), rn(Nn, Wd), rn(Wd), rn(Wd), rn(Wd), rn(Nn, Wd)
+    out_ref, st_ref = torch.empty_like(y), torch.empty(Nn, 2, dtype=F64, device=dev)
+    assert L.gdft_ln_elu_fwd(_lib.stream_ptr(), Nn, Wd, _lib.ptr(y), _lib.ptr(res_), _lib.ptr(scale), _lib.ptr(bias), 1e-6, _lib.ptr(out_ref), _lib.ptr(st_ref)) == 0
+    out, st = go(J.plan_ln_elu_fwd(Nn, Wd, True), [y, res_, scale, bias])
+    assert torch.equal(out, out_ref) and torch.equal(st, st_ref)
+    ws, nb = ws_tensor(_lib.OP_LN_ELU, Nn, Wd, 0, 0, dev)
+    zr, sr, br, yr = torch.empty_like(y), torch.empty_like(scale), torch.empty_like(bias), torch.empty_like(ybias)
+    assert L.gdft_ln_elu_bwd(_lib.stream_ptr(), Nn, Wd, _lib.ptr(y), _lib.ptr(res_), _lib.ptr(scale), _lib.ptr(bias), _lib.ptr(st_ref), _lib.ptr(ob),
+                             _lib.ptr(zr), _lib.ptr(sr), _lib.ptr(br), _lib.wptr(ws), nb) == 0
+    z, s_, b_, _ = go(J.plan_ln_elu_bwd(Nn, Wd, True), [y, res_, scale, bias, st_ref, ob])
+    assert torch.equal(z, zr) and torch.equal(s_, sr) and torch.equal(b_, br)
+    assert L.gdft_dense_ln_elu_fwd(_lib.stream_ptr(), Nn, Wd, _lib.ptr(y), _lib.ptr(ybias), _lib.ptr(res_), _lib.ptr(scale), _lib.ptr(bias), 1e-6,
+                                   _lib.ptr(out_ref), _lib.ptr(st_ref)) == 0
+    out, st = go(J.plan_dense_ln_elu_fwd(Nn, Wd, True, True), [y, ybias, res_, scale, bias])
+    assert torch.equal(out, out_ref) and torch.equal(st, st_ref)
+    assert L.gdft_dense_ln_elu_bwd(_lib.stream_ptr(), Nn, Wd, _lib.ptr(y), _lib.ptr(ybias), _lib.ptr(res_), _lib.ptr(scale), _lib.ptr(bias), _lib.ptr(st_ref),
+                                   _lib.ptr(out_ref), _lib.ptr(ob), _lib.ptr(zr), _lib.ptr(sr), _lib.ptr(br), _lib.ptr(yr), _lib.wptr(ws), nb) == 0
+    z, s_, b_, yb, _ = go(J.plan_dense_ln_elu_bwd(Nn, Wd, True, True, True), [y, ybias, res_, scale, bias, st_ref, out_ref, ob])
+    assert torch.equal(z, zr) and torch.equal(s_, sr) and torch.equal(b_, br) and torch.equal(yb, yr)
+
+    ne = 29
+    A = rn(2, ne, ne)
+    A = A + A.transpose(1, 2)
+    w_ref, V_ref = ops.sym_eigh(A)
+    wv, V = go(J.plan_sym_eigh(2, ne), [A])
+    assert torch.equal(wv, w_ref) and torch.equal(V, V_ref)
+    mm = 7
+    err, fv, x = rn(mm, 2, ne, ne), rn(mm, 2, ne, ne), rn(2, mm)
+    assert torch.equal(go(J.plan_diis_gram(mm, ne), [err])[0], ops.diis_gram(err))
+    assert torch.equal(go(J.plan_diis_combine(mm, ne), [x, fv])[0], ops.diis_combine(x, fv))
+    Nc, nn = 41, 22
+    ao, D, nu = rn(Nc, nn), rn(2, nn, nn), rn(Nc, nn, nn)
+    chi_ref = torch.empty(Nc, 1, 2, nn, dtype=F64, device=dev)
+    ops.chi_contract_(chi_ref, 0, 0, ao, D, nu)
+    assert torch.equal(go(J.plan_chi_contract(Nc, nn), [ao, D, nu])[0], chi_ref[:, 0])
+    assert covered == set(J._TARGETS), set(J._TARGETS) - covered
