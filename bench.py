@@ -555,13 +555,29 @@ def run_xc(ctx, args, key, extras):
     functional = _xc_functional(kind)
     rdm1_dev = molecule.rdm1.clone()
     rdm1_host = rdm1_dev.cpu().pin_memory()
-    payload = torch.empty(1 + 2 * n * n, dtype=torch.float64, device=dev)
-    out_host = torch.empty(1 + 2 * n * n, dtype=torch.float64).pin_memory()
+    # payload [V_xc(2,n,n) | E_xc | pad]: with several ranks it is the exchange buffer of the library's own all-reduce
+    # (gdft_allreduce_fock_p2p over NVLink peer memory); the density VJP's second-stage reduce writes V_xc straight into it
+    n2 = n * n
+    if world > 1:
+        comm = gdist.fock_comm(2 * n2 + 2, dev)
+        payload = comm.buffer[:2 * n2 + 2] if comm is not None else torch.zeros(2 * n2 + 2, dtype=torch.float64, device=dev)
+    else:
+        comm = None
+        payload = torch.zeros(2 * n2 + 2, dtype=torch.float64, device=dev)
+    out_host = torch.empty(2 * n2 + 2, dtype=torch.float64).pin_memory()
 
     def build(rdm1):
-        exc, vxc, _ = gd.xc_energy_and_grads(functional, None, rdm1, molecule, create_graph=False)
+        with ops.density_bwd_into(payload[:2 * n2]):
+            exc, vxc, _ = gd.xc_energy_and_grads(functional, None, rdm1, molecule, create_graph=False)
         if world > 1:
-            exc, vxc = gdist.allreduce_xc(exc, vxc, buf=payload)
+            exc, vxc = gdist.allreduce_xc(exc, vxc)
+            if comm is None:
+                payload[:2 * n2].copy_(vxc.reshape(-1))
+                payload[2 * n2:2 * n2 + 1].copy_(exc.reshape(1))
+        else:
+            if vxc.data_ptr() != payload.data_ptr():
+                payload[:2 * n2].copy_(vxc.reshape(-1))
+            payload[2 * n2:2 * n2 + 1].copy_(exc.reshape(1))
         return exc, vxc
 
     def step_resident():
@@ -569,8 +585,7 @@ def run_xc(ctx, args, key, extras):
 
     def step_e2e():
         rdm1_dev.copy_(rdm1_host, non_blocking=True)
-        exc, vxc = build(rdm1_dev)
-        gdist.pack_xc(exc, vxc, payload) if world == 1 else None
+        build(rdm1_dev)
         out_host.copy_(payload, non_blocking=True)
 
     dgemm_tf, dgemm_ts = ctx.dgemm()
@@ -608,18 +623,20 @@ def run_xc(ctx, args, key, extras):
         del molecule
         torch.cuda.empty_cache()
         if rank == 0:
-            acc = torch.zeros(1 + 2 * n * n, dtype=torch.float64, device=dev)
+            acc = torch.zeros(2 * n2 + 2, dtype=torch.float64, device=dev)
             for r in range(world):
                 m_r = _xc_shard(ctx, key, r)
                 exc, vxc, _ = gd.xc_energy_and_grads(functional, None, m_r.rdm1, m_r, create_graph=False)
-                acc += gdist.pack_xc(exc, vxc)
+                acc[:2 * n2] += vxc.reshape(-1)
+                acc[2 * n2] += exc
                 del m_r, exc, vxc
                 torch.cuda.empty_cache()
             acc = acc.cpu()
-            dE = abs(float(acc[0] - sharded[0]))
-            dV = float((acc[1:] - sharded[1:]).abs().max() / acc[1:].abs().max())
+            dE = abs(float(acc[2 * n2] - sharded[2 * n2]))
+            dV = float((acc[:2 * n2] - sharded[:2 * n2]).abs().max() / acc[:2 * n2].abs().max())
             parity = {"against": f"rank-0 single-GPU recompute of all {world} shards (same kernels, no collective)", "dE_vs_1gpu": dE, "dV_rel": dV,
-                      "E_xc": float(sharded[0]), "tolerance": {"dE": E_TOL, "dV_rel": V_RTOL}, "ok": bool(dE < E_TOL and dV < V_RTOL)}
+                      "E_xc": float(sharded[2 * n2]), "exchange": (comm.backend if comm is not None else "torch.distributed"),
+                      "comm_status": (comm.status() if comm is not None else None), "tolerance": {"dE": E_TOL, "dV_rel": V_RTOL}, "ok": bool(dE < E_TOL and dV < V_RTOL)}
         ctx.barrier()
         if parity is not None and not parity["ok"]:
             ctx.fail(f"{key} x{world}", parity)

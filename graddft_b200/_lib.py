@@ -69,6 +69,22 @@ SIGNATURES = {
     "gdft_chi_contract": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, _P, _P, c_int64]),
     "gdft_fock_assemble": (c_int, [_P, c_int64, _P, _P, _P, c_double, _P]),
     "gdft_fock_add_sym": (c_int, [_P, c_int64, _P, c_double, _P]),
+    "gdft_nccl_available": (c_int, []),
+    "gdft_nccl_unique_id_bytes": (c_size_t, []),
+    "gdft_nccl_unique_id": (c_int, [_P]),
+    "gdft_nccl_comm_create": (c_int, [_P, c_int, c_int, ctypes.POINTER(_P)]),
+    "gdft_nccl_comm_destroy": (c_int, [_P]),
+    "gdft_allreduce_fock": (c_int, [_P, _P, _P, c_size_t]),
+    "gdft_comm_handle_bytes": (c_size_t, []),
+    "gdft_comm_create": (c_int, [c_int, c_int, c_size_t, ctypes.POINTER(_P)]),
+    "gdft_comm_buffer": (_P, [_P]),
+    "gdft_comm_capacity": (c_size_t, [_P]),
+    "gdft_comm_handle": (c_int, [_P, _P]),
+    "gdft_comm_connect": (c_int, [_P, _P]),
+    "gdft_comm_connect_local": (c_int, [_P, ctypes.POINTER(_P)]),
+    "gdft_comm_status": (c_int, [_P, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_ulonglong)]),
+    "gdft_comm_destroy": (c_int, [_P]),
+    "gdft_allreduce_fock_p2p": (c_int, [_P, _P, c_size_t]),
     "gdft_xla_last_status": (c_int, []),
     "gdft_xla_dims_size": (c_size_t, []),
 }

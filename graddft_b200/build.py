@@ -18,7 +18,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = CSRC / "build"
 LIB = HERE / "libgdft_b200.so"
-SOURCES = ["api.cu", "density_fwd.cu", "density_bwd.cu", "pointwise.cu", "eri_integrate.cu", "mlp_epilogue.cu", "dense_gemm.cu", "eigh_jacobi.cu", "eigh_cluster.cu", "chi_contract.cu", "scf_glue.cu", "jax_ffi.cu"]
+SOURCES = ["api.cu", "density_fwd.cu", "density_bwd.cu", "pointwise.cu", "eri_integrate.cu", "mlp_epilogue.cu", "dense_gemm.cu", "eigh_jacobi.cu", "eigh_cluster.cu", "chi_contract.cu", "scf_glue.cu", "allreduce.cu", "jax_ffi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

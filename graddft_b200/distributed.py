@@ -90,15 +90,154 @@ def local_coulomb(P: torch.Tensor, rep_tensor: torch.Tensor, shard: "GridShard")
     return J.reshape(n, n)
 
 
+class _DevicePointer:
+    """Exposes raw device memory of the library to the host framework (no copy): __cuda_array_interface__ v2."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class FockComm:
+    """The exchange step of the sharded path inside the library (`gdft_allreduce_fock*`, include/gdft_b200.h).
+
+    backend "p2p": the library's own one-launch reduce-scatter + all-gather kernel over NVLink peer memory.  The payload
+    (`self.buffer`, a float64 view of IPC-shared device memory owned by the communicator) is ordinary device memory:
+    the density VJP's second-stage reduce and the other partial results are written straight into it
+    (`ops.density_bwd_into`), so nothing is packed or concatenated before the exchange; the call is stream-ordered, needs no
+    host thread and can be captured in a CUDA graph.  Results are bitwise identical on every rank.
+    backend "nccl": in-place `ncclAllReduce` on a communicator the library creates from a broadcast unique id
+    (`gdft_allreduce_fock`, the signature of SURVEY.md 8b), on the same payload view.
+    One process per GPU; handles / ids travel through `torch.distributed` object collectives of `group` (setup only)."""
+
+    def __init__(self, capacity: int, device, group=None, backend: str = "p2p"):
+        from . import _lib
+
+        L = _lib.lib()
+        self.group, self.backend, self.device = group, backend, torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._L, self._comm, self._nccl = L, None, None
+        import ctypes
+
+        with torch.cuda.device(self.device):
+            if backend == "p2p":
+                comm = ctypes.c_void_p()
+                _lib.check(L.gdft_comm_create(self.rank, self.world, int(capacity), ctypes.byref(comm)), "gdft_comm_create")
+                self._comm = comm
+                hb = int(L.gdft_comm_handle_bytes())
+                mine = ctypes.create_string_buffer(hb)
+                _lib.check(L.gdft_comm_handle(comm, mine), "gdft_comm_handle")
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(mine.raw), group=group)
+                _lib.check(L.gdft_comm_connect(comm, ctypes.create_string_buffer(b"".join(handles), hb * self.world)), "gdft_comm_connect")
+                self.capacity = int(L.gdft_comm_capacity(comm))
+                self.buffer = torch.as_tensor(_DevicePointer(int(L.gdft_comm_buffer(comm)), self.capacity), device=self.device)
+                dist.barrier(group=group)  # every rank has opened every peer before the first exchange
+            elif backend == "nccl":
+                if not L.gdft_nccl_available():
+                    raise _lib.GdftError("libnccl.so.2 could not be loaded")
+                nb = int(L.gdft_nccl_unique_id_bytes())
+                ident = ctypes.create_string_buffer(nb)
+                if self.rank == 0:
+                    _lib.check(L.gdft_nccl_unique_id(ident), "gdft_nccl_unique_id")
+                box = [bytes(ident.raw)]
+                dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                comm = ctypes.c_void_p()
+                _lib.check(L.gdft_nccl_comm_create(ctypes.create_string_buffer(box[0], nb), self.rank, self.world, ctypes.byref(comm)), "gdft_nccl_comm_create")
+                self._nccl = comm
+                self.capacity = int(capacity + (capacity & 1))
+                self.buffer = torch.zeros(self.capacity, dtype=torch.float64, device=self.device)
+            else:
+                raise ValueError(f"unknown backend {backend!r}")
+
+    def allreduce(self, count: Optional[int] = None) -> torch.Tensor:
+        """buffer[:count] <- sum over ranks, in place, on the current stream; returns the view."""
+        from . import _lib
+
+        count = self.capacity if count is None else int(count)
+        if self._comm is not None:
+            _lib.check(self._L.gdft_allreduce_fock_p2p(_lib.stream_ptr(), self._comm, count), "gdft_allreduce_fock_p2p")
+        else:
+            _lib.check(self._L.gdft_allreduce_fock(self._nccl, _lib.stream_ptr(), _lib.ptr(self.buffer), count), "gdft_allreduce_fock")
+        return self.buffer[:count]
+
+    def status(self) -> int:
+        """Host-synchronous: 0 ok, 1 some exchange timed out waiting for a peer (p2p backend)."""
+        if self._comm is None:
+            return 0
+        import ctypes
+
+        st, ep = ctypes.c_int(0), ctypes.c_ulonglong(0)
+        self._L.gdft_comm_status(self._comm, ctypes.byref(st), ctypes.byref(ep))
+        return int(st.value)
+
+    def close(self) -> None:
+        if self._comm is not None:
+            torch.cuda.synchronize(self.device)
+            self._L.gdft_comm_destroy(self._comm)
+            self._comm = None
+        if self._nccl is not None:
+            torch.cuda.synchronize(self.device)
+            self._L.gdft_nccl_comm_destroy(self._nccl)
+            self._nccl = None
+
+
+_FOCK_COMMS: Dict[Any, "FockComm"] = {}
+
+
+def fock_comm(capacity: int, device, group=None, backend: Optional[str] = None) -> Optional["FockComm"]:
+    """The process-wide communicator of (group, device), created on first use and grown when a larger payload is asked for.
+    Returns None when the exchange cannot run inside the library (CPU tensors / gloo tests): callers then fall back to
+    `torch.distributed.all_reduce`, which is the host framework's collective, not a different numerical path."""
+    import os
+
+    backend = backend or os.environ.get("GDFT_ALLREDUCE", "p2p")
+    if backend == "torch" or torch.device(device).type != "cuda" or not (dist.is_available() and dist.is_initialized()):
+        return None
+    if dist.get_backend(group) != "nccl":
+        return None
+    key = (id(group) if group is not None else None, torch.device(device).index, backend)
+    c = _FOCK_COMMS.get(key)
+    if c is None or c.capacity < capacity:
+        if c is not None:
+            c.close()
+        c = _FOCK_COMMS[key] = FockComm(max(int(capacity), 1 << 20), device, group, backend)
+    return c
+
+
+def packed_layout(sizes: Sequence[int]) -> Tuple[list, int]:
+    """Offsets of consecutive payload segments, each starting on an even element (16-byte aligned for the 128-bit peer
+    loads/stores of the exchange kernel and the vectorised reduce epilogues); returns (offsets, total)."""
+    offs, off = [], 0
+    for k in sizes:
+        offs.append(off)
+        off += int(k) + (int(k) & 1)
+    return offs, off
+
+
 def allreduce_sum_packed(tensors: Sequence[torch.Tensor], group=None, skip: Sequence[int] = ()):
-    """Sum each tensor over the ranks of `group` with ONE collective on a flat float64 buffer; entries whose index is
-    in `skip` are already complete on every rank and are passed through untouched."""
+    """Sum each tensor over the ranks of `group` with ONE exchange on a flat float64 payload; entries whose index is in
+    `skip` are already complete on every rank and are passed through untouched.  On CUDA with an NCCL process group the
+    exchange runs inside the library (`FockComm`): tensors that already live in their payload segment (see
+    `ops.density_bwd_into`) are not copied, and the returned tensors are VIEWS of the payload, valid until the next exchange.
+    Otherwise (CPU / gloo) the host framework's all_reduce is used."""
     idx = [i for i in range(len(tensors)) if i not in skip]
     if not idx or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return list(tensors)
+    offs, total = packed_layout([tensors[i].numel() for i in idx])
+    comm = fock_comm(total, tensors[idx[0]].device, group)
+    out = list(tensors)
+    if comm is not None:
+        for i, off in zip(idx, offs):
+            seg = comm.buffer[off:off + tensors[i].numel()]
+            if tensors[i].data_ptr() != seg.data_ptr():
+                seg.copy_(tensors[i].reshape(-1))
+        comm.allreduce(total)
+        for i, off in zip(idx, offs):
+            out[i] = comm.buffer[off:off + tensors[i].numel()].reshape(tensors[i].shape)
+        return out
     flat = torch.cat([tensors[i].reshape(-1) for i in idx])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    out, off = list(tensors), 0
+    off = 0
     for i in idx:
         k = tensors[i].numel()
         out[i] = flat[off:off + k].reshape(tensors[i].shape)
@@ -106,8 +245,18 @@ def allreduce_sum_packed(tensors: Sequence[torch.Tensor], group=None, skip: Sequ
     return out
 
 
+def payload_segment(index: int, sizes: Sequence[int], device, group=None) -> Optional[torch.Tensor]:
+    """The payload segment entry `index` of an `allreduce_sum_packed([...])` call with these element counts will occupy
+    (None when the exchange does not run inside the library): hand it to `ops.density_bwd_into`."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    offs, total = packed_layout(sizes)
+    comm = fock_comm(total, device, group)
+    return None if comm is None else comm.buffer[offs[index]:offs[index] + int(sizes[index])]
+
+
 def pack_xc(exc: torch.Tensor, vxc: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[E_xc | V_xc.ravel()] as one contiguous float64 buffer (the all-reduce payload)."""
+    """[E_xc | V_xc.ravel()] as one contiguous float64 buffer."""
     n2 = vxc.numel()
     if out is None:
         out = torch.empty(1 + n2, dtype=vxc.dtype, device=vxc.device)
@@ -121,12 +270,12 @@ def unpack_xc(buf: torch.Tensor, shape) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def allreduce_xc(exc: torch.Tensor, vxc: torch.Tensor, group=None, buf: Optional[torch.Tensor] = None):
-    """Sum the rank-local partial (E_xc, V_xc) over the grid shards: one collective on the packed buffer."""
+    """Sum the rank-local partial (E_xc, V_xc) over the grid shards: one exchange on the payload [V_xc | E_xc]
+    (V_xc first: it is the segment the density VJP writes in place, `payload_segment(0, [vxc.numel(), 1], ...)`)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return exc, vxc
-    buf = pack_xc(exc, vxc, buf)
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    return unpack_xc(buf, vxc.shape)
+    vxc, exc = allreduce_sum_packed([vxc, exc.reshape(1)], group=group)
+    return exc.reshape(()), vxc
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -8,6 +8,8 @@ training through the SCF loop needs (grad_dft/evaluate.py:917-1038).
 """
 from __future__ import annotations
 
+import contextlib
+
 from typing import Optional, Tuple
 
 import torch
@@ -132,10 +134,32 @@ def _density_fwd_raw(basis: PackedBasis, rdm1: torch.Tensor, flags: int):
     return rho, grho, tau, lapl, ehf
 
 
+_BWD_OUT: Optional[torch.Tensor] = None
+
+
+@contextlib.contextmanager
+def density_bwd_into(view: Optional[torch.Tensor]):
+    """The next density VJP (gdft_density_bwd) inside this context writes its [2, n, n] result straight into `view`
+    (2*n*n contiguous float64 elements of device memory, e.g. a segment of the all-reduce payload of
+    `distributed.FockComm`) instead of a fresh tensor: the split-K second-stage reduce becomes the producer of the exchange
+    buffer.  Consumed by the first matching call only; callers check `result.data_ptr()` to see whether it was used."""
+    global _BWD_OUT
+    prev, _BWD_OUT = _BWD_OUT, view
+    try:
+        yield
+    finally:
+        _BWD_OUT = prev
+
+
 def _density_bwd_raw(basis: PackedBasis, flags: int, rho_bar, grho_bar, tau_bar, lapl_bar) -> torch.Tensor:
+    global _BWD_OUT
     L = lib()
     N, dev = basis.N, basis.device
-    out = torch.empty((2, basis.n, basis.n), dtype=F64, device=dev)
+    out = None
+    if _BWD_OUT is not None and _BWD_OUT.numel() == 2 * basis.n * basis.n and _BWD_OUT.device == dev and _BWD_OUT.is_contiguous():
+        out, _BWD_OUT = _BWD_OUT.view(2, basis.n, basis.n), None
+    if out is None:
+        out = torch.empty((2, basis.n, basis.n), dtype=F64, device=dev)
     ws = workspace(L.gdft_workspace_bytes(_lib.OP_DENSITY_BWD, N, basis.n, flags, 0), dev)
     rho_bar, grho_bar, tau_bar, lapl_bar = _c(rho_bar), _c(grho_bar), _c(tau_bar), _c(lapl_bar)
     with _timed("gdft_density_bwd"):

@@ -159,7 +159,15 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
         create_graph = differentiable_fock
         if differentiable_fock and not (torch.is_grad_enabled() and (_requires_grad(params) or atoms.rdm1.requires_grad)):
             create_graph = False
-        exc, fock_xc, at = xc_energy_and_grads(functional, params, atoms.rdm1, atoms, *args, create_graph=create_graph)
+        into = None
+        if shard is not None and atoms.rdm1.is_cuda:
+            from . import distributed as gdist
+            n2 = atoms.rdm1.shape[-1] ** 2
+            nv = int(bool(functional.densitygrads)) + int(bool(functional.coefficient_input_grads))
+            # payload [V_xc | E_xc | J | V_HF...]: the density VJP's second-stage reduce writes V_xc straight into it
+            into = gdist.payload_segment(0, [2 * n2, 1] + ([n2] if shard.eri_row0 is not None else []) + [2 * n2] * nv, atoms.rdm1.device, shard.group)
+        with ops.density_bwd_into(into):
+            exc, fock_xc, at = xc_energy_and_grads(functional, params, atoms.rdm1, atoms, *args, create_graph=create_graph)
         differentiable = fock_xc.requires_grad
         P = atoms.rdm1.sum(dim=0)
         if shard is not None:
@@ -170,8 +178,9 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
             from . import distributed as gdist
             vterms = explicit_terms(params, at, False, *args)
             J = gdist.local_coulomb(P, atoms.rep_tensor, shard)
-            (exc_sum, fock_xc, J, *vterms) = gdist.allreduce_sum_packed(
-                [exc.detach(), fock_xc, J, *vterms], group=shard.group, skip=() if shard.eri_row0 is not None else (2,))
+            (fock_xc, exc_sum, J, *vterms) = gdist.allreduce_sum_packed(
+                [fock_xc, exc.detach().reshape(1), J, *vterms], group=shard.group, skip=() if shard.eri_row0 is not None else (2,))
+            exc_sum = exc_sum.reshape(())
             exc = exc + (exc_sum - exc.detach()) if exc.requires_grad else exc_sum  # value: the global sum; gradient: identity
             EJ = (P * J).sum() / 2.0
         elif differentiable or atoms.rdm1.requires_grad:

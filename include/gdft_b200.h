@@ -297,6 +297,38 @@ int gdft_fock_assemble(gdft_stream_t stream, int64_t n, const double* h1e, const
 int gdft_fock_add_sym(gdft_stream_t stream, int64_t n, const double* V /*[2,n,n]*/, double clip,
                       double* fock /*[2,n,n]*/);
 
+/* ---- the exchange step of the grid-sharded path (not in the reference, which is single-device) ----
+ * One sum over ranks of the packed [V_xc | J | V_HF ... | E_xc] buffer closes a sharded Fock build
+ * (the partial sums of grad_dft/train.py:147-213 computed on each rank's grid rows).
+ *
+ * gdft_allreduce_fock: in-place ncclAllReduce(sum, float64) on the caller's communicator and stream.  libnccl is resolved
+ * with dlopen at first use; gdft_nccl_* create a communicator from a unique id the host side broadcasts. */
+int gdft_nccl_available(void);
+size_t gdft_nccl_unique_id_bytes(void);
+int gdft_nccl_unique_id(void* id_host /*[gdft_nccl_unique_id_bytes()]*/);
+int gdft_nccl_comm_create(const void* id_host, int rank, int world, void** nccl_comm_out);
+int gdft_nccl_comm_destroy(void* nccl_comm);
+int gdft_allreduce_fock(void* nccl_comm /*ncclComm_t*/, gdft_stream_t stream, double* packed /*[count], in place*/, size_t count);
+/* gdft_allreduce_fock_p2p: the library's own exchange kernel over NVLink peer memory.  A communicator owns a payload of
+ * `capacity` doubles in IPC-shareable device memory (gdft_comm_buffer: ordinary device memory, kernels may write their
+ * results straight into it); one launch per rank announces, reduces slice `rank` over all peers in rank order
+ * (reduce-scatter by peer loads), stores the sums into every peer's payload (all-gather by peer stores) and completes a
+ * handshake.  Bitwise identical on all ranks and run to run; no host involvement (CUDA-graph capturable).  gdft_comm_create /
+ * _connect / _destroy are SETUP calls (they allocate and synchronise); handles are exchanged by the host side
+ * (one process per GPU: gdft_comm_handle + gdft_comm_connect; one process driving several GPUs: gdft_comm_connect_local).
+ * Calls on one communicator must be issued in the same order on every rank and never concurrently from two streams. */
+typedef struct gdft_comm gdft_comm;
+size_t gdft_comm_handle_bytes(void);
+int gdft_comm_create(int rank, int world, size_t capacity, gdft_comm** out);
+double* gdft_comm_buffer(gdft_comm* comm);
+size_t gdft_comm_capacity(gdft_comm* comm);
+int gdft_comm_handle(gdft_comm* comm, void* handle_host /*[gdft_comm_handle_bytes()]*/);
+int gdft_comm_connect(gdft_comm* comm, const void* handles_host /*[world][gdft_comm_handle_bytes()], rank order*/);
+int gdft_comm_connect_local(gdft_comm* comm, gdft_comm* const* all /*[world], rank order*/);
+int gdft_comm_status(gdft_comm* comm, int* status_host, unsigned long long* epoch_host); /* host-synchronous */
+int gdft_comm_destroy(gdft_comm* comm);
+int gdft_allreduce_fock_p2p(gdft_stream_t stream, gdft_comm* comm, size_t count);
+
 /* ---- XLA custom-call adapters (graddft_b200/csrc/jax_ffi.cu) --------------------------------------
  * Legacy custom-call ABI void(cudaStream_t, void** buffers, const char* opaque, size_t opaque_len): operands
  * then results in `buffers`, a packed dims struct (gdft_xla_dims_size() bytes; layout in jax_ffi.py) in `opaque`.
