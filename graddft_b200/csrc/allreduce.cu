@@ -110,18 +110,27 @@ __global__ void __launch_bounds__(256) allreduce_fock_kernel(PeerTable peers, in
 #pragma unroll
   for (int p = 0; p < GDFT_COMM_MAX_RANKS; ++p)
     if (p < world) pay[p] = reinterpret_cast<double2*>(peers.base[p] + GDFT_COMM_HEADER_BYTES);
-  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
-    double2 v[GDFT_COMM_MAX_RANKS];
+  // U elements per thread in flight (U x world independent peer loads before the first add: the loop is NVLink-latency-bound)
+  constexpr int U = (WORLD > 0 && WORLD <= 4) ? 4 : 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += U * stride) {
+    double2 v[U][GDFT_COMM_MAX_RANKS];
 #pragma unroll
-    for (int p = 0; p < GDFT_COMM_MAX_RANKS; ++p)
-      if (p < world) v[p] = ld_peer(pay[p] + i);
-    double2 acc = v[0];
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-    for (int p = 1; p < GDFT_COMM_MAX_RANKS; ++p)
-      if (p < world) { acc.x += v[p].x; acc.y += v[p].y; }
+      for (int p = 0; p < GDFT_COMM_MAX_RANKS; ++p)
+        if (p < world && i + u * stride < hi) v[u][p] = ld_peer(pay[p] + i + u * stride);
 #pragma unroll
-    for (int p = 0; p < GDFT_COMM_MAX_RANKS; ++p)
-      if (p < world) st_peer(pay[p] + i, acc);
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride >= hi) break;
+      double2 acc = v[u][0];
+#pragma unroll
+      for (int p = 1; p < GDFT_COMM_MAX_RANKS; ++p)
+        if (p < world) { acc.x += v[u][p].x; acc.y += v[u][p].y; }
+#pragma unroll
+      for (int p = 0; p < GDFT_COMM_MAX_RANKS; ++p)
+        if (p < world) st_peer(pay[p] + i + u * stride, acc);
+    }
   }
 
   // 4. completion: the last CTA of this launch tells every peer that this rank's reads and writes are over and waits for
@@ -303,7 +312,7 @@ extern "C" int gdft_allreduce_fock_p2p(gdft_stream_t stream, gdft_comm* c, size_
   if (count == 0 || c->world == 1) return GDFT_OK;
   const long long count2 = (long long)((count + 1) / 2);  // capacity is even and the tail is owned by the communicator
   const long long per = (count2 + c->world - 1) / c->world;
-  int blocks = (int)imin64(imax64((per + 255) / 256, 1), 32);  // <= 32 CTAs per rank: the exchange is latency-bound
+  int blocks = (int)imin64(imax64((per + 1023) / 1024, 1), 96);  // ~4 elements per thread, <= 96 CTAs per rank: the exchange is latency-bound
   cudaStream_t s = (cudaStream_t)stream;
   switch (c->world) {
     case 2: allreduce_fock_kernel<2><<<blocks, 256, 0, s>>>(c->peers, c->rank, c->world, count2); break;
