@@ -701,9 +701,9 @@ def run_xc(ctx, args, key, extras):
 # second headline metric: jitted-SCF iterations/s (diff_scf_loop = make_jitted_scf_loop, grad_dft/evaluate.py:917)
 # ---------------------------------------------------------------------------------------------------------
 def _scf_tensors(N, n, rank, world, dev, n_omega=1, eri_rows=None):
-    """Rank-local tensors of a synthetic B3LYP/DM21-ready molecule: grid rows seeded per rank, n x n data replicated, the
-    (p,q) rows [r0, r1) of an 8-fold-symmetric PSD rep_tensor built directly as a row block (never materialised whole
-    unless asked for)."""
+    """Rank-local tensors of a synthetic B3LYP/DM21-ready molecule: grid rows seeded per rank, n x n data replicated, and a
+    row block of an 8-fold-symmetric PSD rep_tensor built directly (never materialised whole unless asked for): with several
+    ranks the rank's share of the (p >= q) pair rows, else the (p,q) rows `eri_rows` (default: all)."""
     from graddft_b200 import distributed as gdist
     from graddft_b200.synthetic import synthetic_molecule
 
@@ -714,13 +714,18 @@ def _scf_tensors(N, n, rank, world, dev, n_omega=1, eri_rows=None):
         mol[k] = small[k]
     mol["weights"] = mol["weights"] * ((hi - lo) / N)
     mol["omegas"] = [0.0, 0.4][:n_omega]
-    if eri_rows is None:
-        eri_rows = gdist.shard_bounds(n * n, rank, world, align=32) if world > 1 else (0, n * n)
-    r0, r1 = eri_rows
     g = torch.Generator(device=dev).manual_seed(4242)
     Q = 2 * n
     B = torch.randn(Q, n, n, generator=g, dtype=torch.float64, device=dev)
     B2 = (0.5 * (B + B.transpose(1, 2))).reshape(Q, n * n)
+    if eri_rows is None and world > 1:
+        # this rank's share of the n(n+1)/2 (p >= q) pair rows (balanced; the other half of the rows is their mirror image)
+        p0, p1 = gdist.pair_bounds(n, rank, world)
+        idx = gdist.pair_row_indices(n, p0, p1, dev)
+        mol["rep_tensor"] = (B2[:, idx].T @ B2).div_(Q).reshape(p1 - p0, n, n)
+        del B, B2
+        return mol, p0
+    r0, r1 = eri_rows if eri_rows is not None else (0, n * n)
     mol["rep_tensor"] = (B2[:, r0:r1].T @ B2).div_(Q).reshape(r1 - r0, n, n)
     del B, B2
     return mol, r0
@@ -735,7 +740,7 @@ def _scf_shard(N, n, rank, world, dev, n_omega=1):
         mol["rep_tensor"] = mol["rep_tensor"].reshape(n, n, n, n)
     m = gd.molecule_from_tensors(mol, dev)
     if world > 1:
-        gdist.attach_shard(m, gdist.GridShard(None, rank, world, r0))
+        gdist.attach_shard(m, gdist.GridShard(None, rank, world, None, r0))
     m.packed_basis
     return m
 
@@ -823,6 +828,14 @@ def scf_leg(ctx, shape_key, steps=4, with_parity=True, with_e2e=False):
     if e2e is not None:
         res["e2e"] = e2e
     eri_numel = m.rep_tensor.numel()
+    # bytes one J sweep reads: the packed pair block when the tensor was packed (a quarter of the full rows), else the block as given
+    from graddft_b200 import distributed as _gd
+    _pe = (ops.packed_eri_for(m.rep_tensor, count_use=False) if world == 1 else
+           next((e["packed"] for e in _gd._PACKED_BLOCKS if e["ref"]() is m.rep_tensor), None))
+    eri_sweep_bytes = 8.0 * (_pe.pairs * (_pe.packed.numel() // max(_pe.pairs, 1)) if _pe else eri_numel)
+    eri_packed = bool(_pe)
+    del _pe
+    ops.release_packed_eri()
     del m, out
     torch.cuda.empty_cache()
     if with_parity and world > 1:
@@ -844,19 +857,21 @@ def scf_leg(ctx, shape_key, steps=4, with_parity=True, with_e2e=False):
                 ctx.fail(f"scf_{shape_key} x{world}", parity)
     if rank == 0:
         eri_ms = avg("gdft_eri_jk")
-        eri_bytes = 8.0 * eri_numel
+        eri_bytes = eri_sweep_bytes
         res["kernels_ms"] = {"density_fwd": avg("gdft_density_fwd"), "density_bwd": avg("gdft_density_bwd"), "eri_j": eri_ms,
                              "sym_eigh": avg("gdft_sym_eigh")}
         if eri_bytes > 2.5e8:  # larger than L2: a DRAM figure
             res["roofline_eri"] = {"bound": "hbm", "kernel": "eri_j_kernel (rep_tensor (pq)x(rt) sweep)", "achieved": eri_bytes / eri_ms / 1e6,
                                    "peak": hbm_gbs[0], "unit": "GB/s", "frac": eri_bytes / eri_ms / 1e6 / hbm_gbs[0],
-                                   "bytes_per_launch": eri_bytes, "ms_per_launch": eri_ms, "peak_source": hbm_gbs[1]}
+                                   "bytes_per_launch": eri_bytes, "ms_per_launch": eri_ms, "peak_source": hbm_gbs[1], "packed": eri_packed,
+                                   "unpacked_bytes": 8.0 * n ** 4 / world}
         # roofline of one iteration: B3LYP Fock build = 16 GEMM units (rho, grad, lapl fwd + VJP) + 2 (HF Fock) at the
         # measured DGEMM rate, plus one rep_tensor sweep at the HBM peak (per-GPU shares)
         unit = 2.0 * (N / world) * n * n
         t_roof = 18.0 * unit / (dgemm_tf * 1e9) + eri_bytes / (hbm_gbs[0] * 1e6)
         res["roofline_iter"] = {"ms_at_roofline": t_roof, "frac": t_roof / per_iter,
-                                "model": "18 units x 2*N*n^2 FLOP at measured cuBLAS DGEMM + 8*rows*n^2 B at HBM peak"}
+                                "model": "18 units x 2*N*n^2 FLOP at measured cuBLAS DGEMM + the bytes one J sweep reads (packed pair rows: 8*pairs*npair B; "
+                                         "un-packed: 8*rows*n^2 B) at HBM peak"}
     return res
 
 

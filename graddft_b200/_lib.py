@@ -69,6 +69,12 @@ SIGNATURES = {
     "gdft_chi_contract": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, _P, _P, c_int64]),
     "gdft_fock_assemble": (c_int, [_P, c_int64, _P, _P, _P, c_double, _P]),
     "gdft_fock_add_sym": (c_int, [_P, c_int64, _P, c_double, _P]),
+    "gdft_eri_npair": (c_int64, [c_int64]),
+    "gdft_eri_packed_bytes": (c_size_t, [c_int64, c_int64]),
+    "gdft_eri_packed_workspace": (c_size_t, [c_int64]),
+    "gdft_eri_symmetry_defect": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, c_size_t]),
+    "gdft_eri_pack": (c_int, [_P, c_int64, c_int, c_int64, c_int64, _P, c_int64, c_int64, _P]),
+    "gdft_eri_j_packed": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_nccl_available": (c_int, []),
     "gdft_nccl_unique_id_bytes": (c_size_t, []),
     "gdft_nccl_unique_id": (c_int, [_P]),

@@ -264,14 +264,111 @@ __global__ void fock_add_sym_kernel(int n, const double* __restrict__ V, double 
   fock[idx] = aclip(fock[idx] + (V[idx] + V[s * n * n + j * n + i]), clip);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Packed rep_tensor.  (pq|rt) is symmetric under p<->q and r<->t (grad_dft/interface/pyscf.py builds it with
+// mol.intor("int2e"), aosym s1), so J_pq = sum_{r>=t} (pq|rt) (P_rt + P_tr)(1 - delta_rt/2) needs only the
+// NP = n(n+1)/2 pair rows x NP pair columns: a quarter of the 8 n^4 bytes, re-laid-out ONCE per molecule like the
+// packed basis (packed[pair(p,q)][pair(r,t)], pair(i,j) = i(i+1)/2 + j for i >= j, row pitch NPP = NP rounded up to even,
+// padding column zero).  The sweep is then the plain row-times-vector kernel above on contiguous rows, and because the
+// packed matrix is itself symmetric the transposed sweep (VJP of J w.r.t. P) is the same call.
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline int64_t eri_npair(int64_t n) { return n * (n + 1) / 2; }
+__host__ __device__ inline int64_t eri_npair_pad(int64_t n) { return (eri_npair(n) + 1) & ~int64_t(1); }
+
+__device__ __forceinline__ void pair_decode(int64_t pr, int& i, int& j) {
+  // i = floor((sqrt(8 pr + 1) - 1) / 2), corrected for rounding
+  int64_t ii = (int64_t)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);
+  while (ii * (ii + 1) / 2 > pr) --ii;
+  while ((ii + 1) * (ii + 2) / 2 <= pr) ++ii;
+  i = (int)ii;
+  j = (int)(pr - ii * (ii + 1) / 2);
+}
+
+// one CTA per pair row: packed[pr - pair0][pair(k,l)] = src_row(pr)[k][l], k >= l
+// src_mode 0: src holds the rows (p,q) = src_row0 .. of the full tensor, 1: src holds exactly the pair rows pair0 ..
+__global__ void __launch_bounds__(256) eri_pack_kernel(int n, int64_t pair0, int64_t pairs, int src_mode, int64_t src_row0,
+                                                       const double* __restrict__ src, double* __restrict__ packed) {
+  const int64_t NPP = eri_npair_pad(n), NP = eri_npair(n);
+  for (int64_t lp = blockIdx.x; lp < pairs; lp += gridDim.x) {
+    int i, j;
+    pair_decode(pair0 + lp, i, j);
+    const double* row = src + (src_mode ? lp : ((int64_t)i * n + j - src_row0)) * (int64_t)n * n;
+    double* out = packed + lp * NPP;
+    for (int k = threadIdx.x >> 5; k < n; k += 8) {
+      const double* rk = row + (int64_t)k * n;
+      double* ok = out + (int64_t)k * (k + 1) / 2;
+      for (int l = threadIdx.x & 31; l <= k; l += 32) ok[l] = __ldcs(rk + l);
+    }
+    if (threadIdx.x == 0 && NPP > NP) out[NP] = 0.0;
+  }
+}
+
+// part[blockIdx.x] = {max |asymmetry|, max |value|} over the rows this CTA visits (rows (p,q) = row0 .. row0+rows-1)
+__global__ void __launch_bounds__(256) eri_symmetry_kernel(int n, int64_t row0, int64_t rows, const double* __restrict__ src,
+                                                           double* __restrict__ part) {
+  double asym = 0.0, big = 0.0;
+  const int64_t R1 = row0 + rows;
+  for (int64_t lr = blockIdx.x; lr < rows; lr += gridDim.x) {
+    const int64_t r = row0 + lr;
+    const int p = (int)(r / n), q = (int)(r % n);
+    const double* row = src + lr * (int64_t)n * n;
+    const int64_t rt = (int64_t)q * n + p;  // the (q,p) row, when this block holds it
+    const double* rowT = (rt >= row0 && rt < R1 && q < p) ? src + (rt - row0) * (int64_t)n * n : nullptr;
+    for (int64_t c = threadIdx.x; c < (int64_t)n * n; c += 256) {
+      const int k = (int)(c / n), l = (int)(c % n);
+      const double v = row[c];
+      big = fmax(big, fabs(v));
+      if (l < k) asym = fmax(asym, fabs(v - row[(int64_t)l * n + k]));
+      if (rowT) asym = fmax(asym, fabs(v - rowT[c]));
+    }
+  }
+  __shared__ double sa[256], sb[256];
+  sa[threadIdx.x] = asym; sb[threadIdx.x] = big;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sa[threadIdx.x] = fmax(sa[threadIdx.x], sa[threadIdx.x + o]); sb[threadIdx.x] = fmax(sb[threadIdx.x], sb[threadIdx.x + o]); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = sa[0]; part[2 * blockIdx.x + 1] = sb[0]; }
+}
+__global__ void eri_symmetry_final_kernel(int nparts, const double* __restrict__ part, double* __restrict__ out2) {
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 32) { a = fmax(a, part[2 * i]); b = fmax(b, part[2 * i + 1]); }
+  for (int o = 16; o > 0; o >>= 1) { a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+  if (threadIdx.x == 0) { out2[0] = a; out2[1] = b; }
+}
+
+// Ppk[pair(k,l)] = P[k][l] + P[l][k] (k > l), P[k][k] (k == l); padding 0
+__global__ void eri_pack_p_kernel(int n, const double* __restrict__ P, double* __restrict__ Ppk) {
+  const int64_t NPP = eri_npair_pad(n), NP = eri_npair(n);
+  const int64_t pr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pr >= NPP) return;
+  if (pr >= NP) { Ppk[pr] = 0.0; return; }
+  int k, l;
+  pair_decode(pr, k, l);
+  Ppk[pr] = (k == l) ? P[(int64_t)k * n + k] : P[(int64_t)k * n + l] + P[(int64_t)l * n + k];
+}
+// J[i][j] = J[j][i] = Jpk[pair(i,j) - pair0] for the local pairs; every other entry 0 (so that partial J's sum to the whole)
+__global__ void eri_unpack_j_kernel(int n, int64_t pair0, int64_t pairs, const double* __restrict__ Jpk, double* __restrict__ J) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * n) return;
+  const int a = (int)(idx / n), b = (int)(idx % n);
+  const int i = a > b ? a : b, j = a > b ? b : a;
+  const int64_t pr = (int64_t)i * (i + 1) / 2 + j - pair0;
+  J[idx] = (pr >= 0 && pr < pairs) ? Jpk[pr] : 0.0;
+}
+
 }  // namespace gdft
 
 using namespace gdft;
 
 // Row block [row0, row0+rows) of the (pq) x (rt) sweep: `eri_rows` points at the block's first row.  The per-row
 // summation order does not depend on the blocking, so a row-sharded J is bitwise equal to the unsharded one.
+static int eri_gemv_launch(cudaStream_t stream, int64_t C, int64_t rows, const double* eri_rows, const double* P, double* J_rows);
 static int eri_j_rows_launch(cudaStream_t stream, int64_t n, int64_t rows, const double* eri_rows, const double* P, double* J_rows) {
-  const int64_t C = n * n;
+  return eri_gemv_launch(stream, n * n, rows, eri_rows, P, J_rows);
+}
+static int eri_gemv_launch(cudaStream_t stream, int64_t C, int64_t rows, const double* eri_rows, const double* P, double* J_rows) {
   const bool vec = (C % 2 == 0) && aligned16(eri_rows);
   const bool small = (rows + 31) / 32 < 2 * 148;  // fewer than two CTAs per SM at four rows per warp
   const int64_t nblocks = small ? (rows + 7) / 8 : (rows + 31) / 32;
@@ -284,6 +381,69 @@ static int eri_j_rows_launch(cudaStream_t stream, int64_t n, int64_t rows, const
     else eri_j_kernel<false, 4><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
   }
   GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+// ---- packed rep_tensor entry points -----------------------------------------------------------------------------------
+extern "C" int64_t gdft_eri_npair(int64_t n) { return n > 0 ? eri_npair(n) : 0; }
+extern "C" size_t gdft_eri_packed_bytes(int64_t n, int64_t pairs) { return (n > 0 && pairs > 0) ? (size_t)pairs * (size_t)eri_npair_pad(n) * 8 : 0; }
+extern "C" size_t gdft_eri_packed_workspace(int64_t n) { return n > 0 ? (size_t)(2 * eri_npair_pad(n) + 2 * 148 * 8 + 64) * 8 : 0; }
+
+extern "C" int gdft_eri_symmetry_defect(gdft_stream_t stream_, int64_t n, int64_t row0, int64_t rows, const double* eri_rows, double* out2,
+                                        void* ws, size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || n > 2048 || row0 < 0 || rows <= 0 || row0 + rows > n * n) return GDFT_BAD_SHAPE;
+  if (!eri_rows || !out2) return GDFT_BAD_ARGUMENT;
+  if (ws_bytes < gdft_eri_packed_workspace(n)) return GDFT_WORKSPACE_TOO_SMALL;
+  const int nparts = (int)imin64(rows, 148 * 8);
+  double* part = static_cast<double*>(ws);
+  eri_symmetry_kernel<<<nparts, 256, 0, stream>>>((int)n, row0, rows, eri_rows, part);
+  GDFT_LAUNCH_CHECK();
+  eri_symmetry_final_kernel<<<1, 32, 0, stream>>>(nparts, part, out2);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+extern "C" int gdft_eri_pack(gdft_stream_t stream_, int64_t n, int src_is_pair_rows, int64_t src_row0, int64_t src_rows, const double* src,
+                             int64_t pair0, int64_t pairs, double* packed) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || n > 2048 || pair0 < 0 || pairs <= 0 || pair0 + pairs > eri_npair(n)) return GDFT_BAD_SHAPE;
+  if (!src || !packed) return GDFT_BAD_ARGUMENT;
+  if (!aligned16(packed)) return GDFT_BAD_ALIGNMENT;
+  if (src_is_pair_rows) {
+    if (src_rows != pairs) return GDFT_BAD_SHAPE;
+  } else {
+    // first and last pair rows must lie inside the source block (rows in between do, the map pair -> row is increasing)
+    auto row_of = [&](int64_t pr) { int64_t i = (int64_t)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5); while (i * (i + 1) / 2 > pr) --i; while ((i + 1) * (i + 2) / 2 <= pr) ++i; return i * n + (pr - i * (i + 1) / 2); };
+    if (src_row0 < 0 || src_rows <= 0 || row_of(pair0) < src_row0 || row_of(pair0 + pairs - 1) >= src_row0 + src_rows) return GDFT_BAD_SHAPE;
+  }
+  eri_pack_kernel<<<(unsigned)imin64(pairs, 148 * 16), 256, 0, stream>>>((int)n, pair0, pairs, src_is_pair_rows ? 1 : 0, src_row0, src, packed);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+// J[n,n] from the packed pair rows [pair0, pair0 + pairs): entries of other pairs are written as zero.  EJ (optional) is
+// 1/2 <P, J> of what was written (the whole E_J when pairs == npair).
+extern "C" int gdft_eri_j_packed(gdft_stream_t stream_, int64_t n, int64_t pair0, int64_t pairs, const double* packed, const double* P, double* J,
+                                 double* EJ, void* ws, size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || n > 2048 || pair0 < 0 || pairs < 0 || pair0 + pairs > eri_npair(n)) return GDFT_BAD_SHAPE;
+  if (!packed || !P || !J) return GDFT_BAD_ARGUMENT;
+  if (!aligned16(packed) || !aligned16(ws)) return GDFT_BAD_ALIGNMENT;
+  if (ws_bytes < gdft_eri_packed_workspace(n)) return GDFT_WORKSPACE_TOO_SMALL;
+  const int64_t NPP = eri_npair_pad(n);
+  double* Ppk = static_cast<double*>(ws);
+  double* Jpk = Ppk + NPP;
+  eri_pack_p_kernel<<<(unsigned)((NPP + 255) / 256), 256, 0, stream>>>((int)n, P, Ppk);
+  GDFT_LAUNCH_CHECK();
+  if (pairs > 0)
+    if (int rc = eri_gemv_launch(stream, NPP, pairs, packed, Ppk, Jpk)) return rc;
+  eri_unpack_j_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, stream>>>((int)n, pair0, pairs, Jpk, J);
+  GDFT_LAUNCH_CHECK();
+  if (EJ) {
+    dot_kernel<<<1, 1024, 0, stream>>>(n * n, P, J, 0.5, EJ);
+    GDFT_LAUNCH_CHECK();
+  }
   return GDFT_OK;
 }
 

@@ -29,10 +29,26 @@ def shard_bounds(N: int, rank: int, world: int, align: int = 128) -> Tuple[int, 
 _ROW_FIELDS = ("ao", "grad_ao", "grad_n_ao2", "chi", "weights", "coords")
 
 
-def shard_molecule_tensors(mol: Dict[str, torch.Tensor], rank: int, world: int, shard_eri: bool = False) -> Dict[str, torch.Tensor]:
+def pair_bounds(n: int, rank: int, world: int, align: int = 32) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of the n(n+1)/2 (p >= q) pair rows of a pair-symmetric rep_tensor for rank `rank`."""
+    return shard_bounds(n * (n + 1) // 2, rank, world, align=align)
+
+
+def pair_row_indices(n: int, lo: int, hi: int, device=None) -> torch.Tensor:
+    """Flattened (p,q) row index p*n + q (p >= q) of the pairs lo .. hi-1 in pair order pair(p,q) = p(p+1)/2 + q."""
+    pr = torch.arange(lo, hi, dtype=torch.int64, device=device)
+    p = ((torch.sqrt(8.0 * pr.to(torch.float64) + 1.0) - 1.0) * 0.5).floor().to(torch.int64)
+    p = torch.where(p * (p + 1) // 2 > pr, p - 1, p)
+    p = torch.where((p + 1) * (p + 2) // 2 <= pr, p + 1, p)
+    return p * n + (pr - p * (p + 1) // 2)
+
+
+def shard_molecule_tensors(mol: Dict[str, torch.Tensor], rank: int, world: int, shard_eri=False) -> Dict[str, torch.Tensor]:
     """The rank's row block of every grid-sized tensor; everything else is passed through (replicated).  With
-    `shard_eri` the (p,q) rows of rep_tensor are split as well: `rep_tensor` becomes the block [rows, n, n] and
-    `eri_row0` its first row (at n = 400 the tensor is 205 GB and cannot be replicated)."""
+    `shard_eri` the rows of rep_tensor are split as well (at n = 400 the tensor is 205 GB and cannot be replicated):
+    True / "rows": `rep_tensor` becomes the contiguous block [rows, n, n] of (p,q) rows and `eri_row0` its first row;
+    "pairs": `rep_tensor` becomes the block of (p >= q) rows of this rank's share of the n(n+1)/2 pair rows and `eri_pair0`
+    its first pair -- half the rows, evenly balanced, for pair-symmetric tensors (what the packed sweep needs)."""
     N = int(mol["weights"].shape[0])
     lo, hi = shard_bounds(N, rank, world)
     out = dict(mol)
@@ -42,9 +58,14 @@ def shard_molecule_tensors(mol: Dict[str, torch.Tensor], rank: int, world: int, 
     if shard_eri and out.get("rep_tensor") is not None:
         eri = out["rep_tensor"]
         n = int(eri.shape[-1])
-        r0, r1 = shard_bounds(n * n, rank, world, align=32)  # 32 rows = one CTA pass of the sweep kernel
-        out["rep_tensor"] = eri.reshape(n * n, n, n)[r0:r1].contiguous()
-        out["eri_row0"] = r0
+        if shard_eri == "pairs":
+            p0, p1 = pair_bounds(n, rank, world)
+            out["rep_tensor"] = eri.reshape(n * n, n, n)[pair_row_indices(n, p0, p1, eri.device)].contiguous()
+            out["eri_pair0"] = p0
+        else:
+            r0, r1 = shard_bounds(n * n, rank, world, align=32)  # 32 rows = one CTA pass of the sweep kernel
+            out["rep_tensor"] = eri.reshape(n * n, n, n)[r0:r1].contiguous()
+            out["eri_row0"] = r0
     return out
 
 
@@ -58,6 +79,11 @@ class GridShard:
     rank: int
     world: int
     eri_row0: Optional[int] = None
+    eri_pair0: Optional[int] = None  # rep_tensor holds the (p >= q) rows of the pairs [eri_pair0, eri_pair0 + rep_tensor.shape[0])
+
+    @property
+    def eri_sharded(self) -> bool:
+        return self.eri_row0 is not None or self.eri_pair0 is not None
 
 
 def attach_shard(molecule, shard: "GridShard"):
@@ -73,17 +99,64 @@ def shard_molecule(mol: Dict[str, torch.Tensor], rank: int, world: int, device=N
     from .molecule import molecule_from_tensors
 
     part = shard_molecule_tensors(mol, rank, world, shard_eri=shard_eri)
-    return attach_shard(molecule_from_tensors(part, device), GridShard(group, rank, world, part.get("eri_row0")))
+    return attach_shard(molecule_from_tensors(part, device), GridShard(group, rank, world, part.get("eri_row0"), part.get("eri_pair0")))
+
+
+_PACKED_BLOCKS: list = []
+
+
+def _packed_block(rep_tensor: torch.Tensor, n: int, shard: "GridShard"):
+    """Packed form of this rank's rep_tensor block (pair-symmetric columns; for a (p,q)-row block also only its p >= q rows),
+    built at the block's second use like `ops.packed_eri_for`; None when packing is off, refused or not yet due."""
+    import os
+    from . import ops
+
+    mode = os.environ.get("GDFT_PACK_ERI", "auto")
+    if mode == "never" or not rep_tensor.is_cuda or n < ops.PACK_ERI_MIN_N:
+        return None
+    entry = ops._cache_entry(_PACKED_BLOCKS, rep_tensor, (shard.eri_row0, shard.eri_pair0), limit=4)
+    if entry["packed"] is not None:
+        return entry["packed"] or None
+    entry["uses"] += 1
+    if (mode != "always" and entry["uses"] < 2) or torch.cuda.is_current_stream_capturing():
+        return None
+    try:
+        if shard.eri_pair0 is not None:
+            # pair rows: only the column symmetry can be checked locally (row symmetry is the caller's statement)
+            rows = int(rep_tensor.shape[0])
+            col = rep_tensor - rep_tensor.transpose(1, 2) if rows * n * n <= (1 << 28) else None
+            ok = True if col is None else bool(float(col.abs().max()) <= ops.ERI_SYMMETRY_RTOL * float(rep_tensor.abs().max()))
+            del col
+            entry["packed"] = ops.PackedERI.from_pair_rows(rep_tensor, n, shard.eri_pair0) if ok else False
+        else:
+            asym, big = ops.eri_symmetry_defect(rep_tensor, n, shard.eri_row0)
+            entry["packed"] = ops.PackedERI.from_rows(rep_tensor, n, shard.eri_row0) if asym <= ops.ERI_SYMMETRY_RTOL * big else False
+    except torch.OutOfMemoryError:
+        entry["packed"] = False
+    return entry["packed"] or None
 
 
 def local_coulomb(P: torch.Tensor, rep_tensor: torch.Tensor, shard: "GridShard") -> torch.Tensor:
-    """J as this rank can compute it: the full matrix when rep_tensor is replicated, else its own (p,q) rows written
-    into a zero matrix (the all-reduce that follows assembles the rest)."""
+    """J as this rank can compute it: the full matrix when rep_tensor is replicated, else the entries of its own rows
+    written into a zero matrix (the all-reduce that follows assembles the rest).  Row blocks of a pair-symmetric tensor
+    go through the packed sweep from their second use on (a quarter of the bytes; see include/gdft_b200.h)."""
     from . import ops
 
-    if shard.eri_row0 is None:
-        return ops.coulomb_j(P, rep_tensor)
+    if not shard.eri_sharded:
+        return ops.coulomb_j_auto(P, rep_tensor)
     n = int(P.shape[0])
+    pe = _packed_block(rep_tensor, n, shard)
+    if pe is not None:
+        return pe.coulomb(P)
+    if shard.eri_pair0 is not None:
+        # un-packed pair rows: the plain row sweep, scattered to both triangles
+        rows = int(rep_tensor.shape[0])
+        idx = pair_row_indices(n, shard.eri_pair0, shard.eri_pair0 + rows, P.device)
+        vals = ops.coulomb_j_rows(P, rep_tensor)
+        J = torch.zeros(n * n, dtype=P.dtype, device=P.device)
+        J[idx] = vals
+        J[(idx % n) * n + idx // n] = vals
+        return J.reshape(n, n)
     J = torch.zeros(n * n, dtype=P.dtype, device=P.device)
     rows = int(rep_tensor.shape[0])
     J[shard.eri_row0:shard.eri_row0 + rows] = ops.coulomb_j_rows(P, rep_tensor)
@@ -212,6 +285,16 @@ def packed_layout(sizes: Sequence[int]) -> Tuple[list, int]:
         offs.append(off)
         off += int(k) + (int(k) & 1)
     return offs, off
+
+
+def exchange_is_capturable(device, group=None) -> bool:
+    """True when `allreduce_sum_packed` on `device` runs as the library's peer-memory kernel (backend "p2p"): stream-ordered,
+    no host thread, device-resident epochs -- the only exchange a CUDA graph of the sharded SCF loop may contain."""
+    import os
+
+    if os.environ.get("GDFT_ALLREDUCE", "p2p") != "p2p" or torch.device(device).type != "cuda":
+        return False
+    return bool(dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl")
 
 
 def allreduce_sum_packed(tensors: Sequence[torch.Tensor], group=None, skip: Sequence[int] = ()):

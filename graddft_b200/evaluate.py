@@ -359,8 +359,9 @@ class _GraphedLoop:
     handle and workspace, captures one more run into a `torch.cuda.CUDAGraph`, and every later call with the same
     tensors is a single graph launch that reads their CURRENT contents (update rdm1 / params in place between calls).
     The returned Molecule is the captured one: its tensors are overwritten by the next replay, clone what must be kept.
-    Falls back to the eager loop whenever a capture is impossible: gradients requested, a grid-sharded molecule, or an
-    eigenproblem too large for the status-word-free solver (n > gdft_sym_eigh_max_n: cuSOLVER's eigh synchronises)."""
+    Falls back to the eager loop whenever a capture is impossible: gradients requested, a grid-sharded molecule whose
+    exchange step is not the library's peer-memory kernel, or an eigenproblem too large for the status-word-free solvers
+    (n > gdft_sym_eigh_max_n: cuSOLVER's eigh synchronises)."""
 
     MAX_ENTRIES = 8
 
@@ -384,8 +385,15 @@ class _GraphedLoop:
         from .train import _requires_grad
         n = molecule.s1e.shape[-1]
         wants_grad = torch.is_grad_enabled() and (_requires_grad(params) or molecule.rdm1.requires_grad)
-        if (args or wants_grad or not molecule.rdm1.is_cuda or "_shard" in molecule.__dict__
-                or n > ops.lib().gdft_sym_eigh_max_n()):
+        shard = molecule.__dict__.get("_shard")
+        if shard is not None:
+            # a grid-sharded loop is capturable when its exchange step is the library's own peer-memory kernel (device-side
+            # epochs, no host thread, no NCCL call inside the capture): every rank captures and replays the same graph
+            from . import distributed as gdist
+            sharded_ok = gdist.exchange_is_capturable(molecule.rdm1.device, shard.group)
+        else:
+            sharded_ok = True
+        if (args or wants_grad or not molecule.rdm1.is_cuda or not sharded_ok or n > ops.lib().gdft_sym_eigh_max_n()):
             self.last_call_was_graph = False
             return self.loop(params, molecule, *args)
         ts = self._tensors(params, molecule)

@@ -149,7 +149,7 @@ def HF_coefficient_input_grad_2_Fock(grid, functional, params, chi: Array, ao: A
 def coulomb_potential(rdm1: Array, rep_tensor: Array, precision=None) -> Array:
     """J[p,q] = sum_rt (pq|rt) P[r,t] -- grad_dft/molecule.py:788-811 (rdm1 is the spin-summed [n,n] matrix)."""
     _check("rdm1", rdm1, 2), _check("rep_tensor", rep_tensor, 4)
-    return ops.coulomb_j(rdm1, rep_tensor)
+    return ops.coulomb_j_auto(rdm1, rep_tensor)
 
 
 def coulomb_energy(rdm1: Array, rep_tensor: Array, precision=None) -> Array:

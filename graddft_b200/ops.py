@@ -373,8 +373,195 @@ def coulomb_k(P: torch.Tensor, eri: torch.Tensor) -> torch.Tensor:
 
 def coulomb_j_and_energy(P: torch.Tensor, eri: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """J and E_J = 1/2 <P,J> from one sweep (non-differentiable fast path used by the predictor)."""
+    pe = packed_eri_for(eri)
+    if pe is not None:
+        return pe.coulomb(P.detach(), want_energy=True)
     J, EJ = _eri_j_raw(P.detach(), eri.detach(), want_energy=True)
     return J, EJ[0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# packed rep_tensor: the pair-symmetric quarter of the ERI sweep, laid out once per molecule (like the packed basis)
+# ---------------------------------------------------------------------------------------------------------
+ERI_SYMMETRY_RTOL = 1e-13  # max |asymmetry| / max |value| below which a rep_tensor counts as pair-symmetric
+
+
+def eri_symmetry_defect(eri_rows: torch.Tensor, n: int, row0: int = 0) -> Tuple[float, float]:
+    """(max |(pq|rt) - (pq|tr)| and |(pq|rt) - (qp|rt)| where both rows are present, max |(pq|rt)|) over the (p,q) rows
+    [row0, row0 + rows) -- host-synchronous, a setup call."""
+    L = lib()
+    eri_rows = _c(eri_rows)
+    rows = eri_rows.numel() // (n * n)
+    out = torch.empty(2, dtype=F64, device=eri_rows.device)
+    ws = workspace(L.gdft_eri_packed_workspace(n), eri_rows.device)
+    check(L.gdft_eri_symmetry_defect(stream_ptr(), n, int(row0), rows, ptr(eri_rows), ptr(out), wptr(ws), ws.numel()), "gdft_eri_symmetry_defect")
+    a, b = out.tolist()
+    return a, b
+
+
+class PackedERI:
+    """Pair rows [pair0, pair0 + pairs) of a pair-symmetric rep_tensor as packed[pairs][npair_pad] (include/gdft_b200.h,
+    "packed rep_tensor").  `complete` = all n(n+1)/2 pair rows are here (single-GPU molecule)."""
+
+    def __init__(self, packed: torch.Tensor, n: int, pair0: int, pairs: int, exchange_symmetric: bool = False):
+        self.packed, self.n, self.pair0, self.pairs = packed, int(n), int(pair0), int(pairs)
+        self.npair = int(lib().gdft_eri_npair(n))
+        self.complete = pair0 == 0 and pairs == self.npair
+        self.exchange_symmetric = exchange_symmetric  # (pq|rt) == (rt|pq) verified: the transposed sweep is the sweep itself
+
+    @staticmethod
+    def _alloc(n: int, pairs: int, device) -> torch.Tensor:
+        return torch.empty(int(lib().gdft_eri_packed_bytes(n, pairs)) // 8, dtype=F64, device=device)
+
+    @classmethod
+    def from_rows(cls, eri_rows: torch.Tensor, n: int, row0: int = 0) -> "PackedERI":
+        """From a contiguous block of (p,q) rows (the whole tensor: row0 = 0, n*n rows): the pair rows whose (p >= q) source
+        row lies inside the block -- a contiguous pair range, because pair(i,j) -> i*n + j is increasing."""
+        eri_rows = _c(eri_rows)
+        rows = eri_rows.numel() // (n * n)
+        r1 = row0 + rows
+
+        def first_pair_at_or_after(r):  # smallest pair index whose row i*n+j (j <= i) is >= r
+            i, j = divmod(r, n)
+            if i >= n:
+                return n * (n + 1) // 2
+            return i * (i + 1) // 2 + j if j <= i else (i + 1) * (i + 2) // 2
+
+        pair0, pair1 = first_pair_at_or_after(row0), first_pair_at_or_after(r1)
+        pairs = pair1 - pair0
+        packed = cls._alloc(n, max(pairs, 1), eri_rows.device)
+        if pairs > 0:
+            check(lib().gdft_eri_pack(stream_ptr(), n, 0, int(row0), rows, ptr(eri_rows), pair0, pairs, ptr(packed)), "gdft_eri_pack")
+        return cls(packed, n, pair0, pairs)
+
+    @classmethod
+    def from_pair_rows(cls, block: torch.Tensor, n: int, pair0: int) -> "PackedERI":
+        """From a block that holds exactly the (p >= q) rows of the pairs [pair0, pair0 + block.shape[0]) (balanced sharding)."""
+        block = _c(block)
+        pairs = block.numel() // (n * n)
+        packed = cls._alloc(n, max(pairs, 1), block.device)
+        if pairs > 0:
+            check(lib().gdft_eri_pack(stream_ptr(), n, 1, 0, pairs, ptr(block), int(pair0), pairs, ptr(packed)), "gdft_eri_pack")
+        return cls(packed, n, pair0, pairs)
+
+    def coulomb(self, P: torch.Tensor, want_energy: bool = False):
+        """J[n,n] of the local pair rows (zero elsewhere unless complete) and, optionally, 1/2 <P, J>."""
+        L = lib()
+        P = _c(P)
+        n = self.n
+        if tuple(P.shape) != (n, n):
+            raise TypeError(f"rdm1 must be [{n}, {n}], got {tuple(P.shape)}")
+        J = torch.empty((n, n), dtype=F64, device=P.device)
+        EJ = torch.empty((1,), dtype=F64, device=P.device) if want_energy else None
+        ws = workspace(L.gdft_eri_packed_workspace(n), P.device)
+        with _timed("gdft_eri_jk"):
+            check(L.gdft_eri_j_packed(stream_ptr(), n, self.pair0, self.pairs, ptr(self.packed), ptr(P), ptr(J), ptr(EJ), wptr(ws), ws.numel()),
+                  "gdft_eri_j_packed")
+        return (J, EJ[0]) if want_energy else J
+
+
+class _CoulombJPacked(Function):
+    """J through the packed sweep.  With the exchange symmetry (pq|rt) = (rt|pq) verified the operator is self-adjoint and
+    its VJP is the same call; otherwise the transposed sweep of the original tensor supplies it."""
+
+    @staticmethod
+    def forward(ctx, P, pe, eri):
+        ctx.pe, ctx.eri = pe, eri
+        return pe.coulomb(P)
+
+    @staticmethod
+    def backward(ctx, Jbar):
+        pe = ctx.pe
+        if not pe.complete:
+            raise NotImplementedError("the VJP of a partial (sharded) packed sweep is not bound: the sharded predictor is first order")
+        if pe.exchange_symmetric:
+            return _CoulombJPacked.apply(Jbar, pe, ctx.eri), None, None
+        return _CoulombJT.apply(Jbar, ctx.eri), None, None
+
+
+_PACKED_ERI: list = []
+PACK_ERI_MIN_N = 16
+
+
+def _cache_entry(cache: list, tensor: torch.Tensor, extra: tuple, limit: int = 6) -> dict:
+    """The cache entry of THIS tensor object at its current version counter (weak reference: an address reused by another
+    tensor after this one died can never hit), created on first sight; the oldest entries are dropped beyond `limit`."""
+    import weakref
+
+    cache[:] = [e for e in cache if e["ref"]() is not None]
+    for e in cache:
+        if e["ref"]() is tensor and e["version"] == tensor._version and e["extra"] == extra:
+            return e
+    e = {"ref": weakref.ref(tensor), "version": tensor._version, "extra": extra, "uses": 0, "packed": None}
+    cache.append(e)
+    del cache[:-limit]
+    return e
+
+
+def packed_eri_for(eri: torch.Tensor, count_use: bool = True) -> Optional[PackedERI]:
+    """The packed form of a FULL rep_tensor [n,n,n,n], or None.  Policy (env GDFT_PACK_ERI = auto | always | never): `auto`
+    packs a tensor at its SECOND use (a one-off J pays one sweep, an SCF loop or a training run pays a quarter of a sweep
+    per build from then on); packing checks the pair symmetries on the device first (two extra sweeps, host-synchronous,
+    once per tensor) and is skipped for tensors that are not symmetric to ERI_SYMMETRY_RTOL.  Never packs during CUDA-graph
+    capture.  Keyed by the tensor OBJECT (weak reference) and its version counter: in-place edits invalidate the packed copy,
+    and a new tensor that happens to reuse a dead tensor's address can never pick it up."""
+    import os
+
+    mode = os.environ.get("GDFT_PACK_ERI", "auto")
+    if mode == "never" or eri is None or not eri.is_cuda or eri.dim() != 4 or eri.dtype != F64:
+        return None
+    n = int(eri.shape[-1])
+    if tuple(eri.shape) != (n, n, n, n) or n < PACK_ERI_MIN_N:
+        return None
+    entry = _cache_entry(_PACKED_ERI, eri, ())
+    if entry["packed"] is not None:
+        return entry["packed"] or None  # False: examined and refused
+    if count_use:
+        entry["uses"] += 1
+    if (mode != "always" and entry["uses"] < 2) or torch.cuda.is_current_stream_capturing():
+        return None
+    try:
+        e = _c(eri.detach())
+        asym, big = eri_symmetry_defect(e, n, 0)
+        if not (asym <= ERI_SYMMETRY_RTOL * big):
+            entry["packed"] = False
+            return None
+        pe = PackedERI.from_rows(e, n, 0)
+        # exchange symmetry of the packed matrix itself: (ij|kl) == (kl|ij)
+        sq = pe.packed.view(pe.pairs, -1)[:, :pe.npair]
+        pe.exchange_symmetric = bool(float((sq - sq.T).abs().max()) <= ERI_SYMMETRY_RTOL * big) if pe.npair <= 8192 else _exchange_symmetric_blocked(sq, big)
+        entry["packed"] = pe
+        return pe
+    except torch.OutOfMemoryError:
+        entry["packed"] = False
+        return None
+
+
+def release_packed_eri() -> None:
+    """Drop every cached packed rep_tensor (they are otherwise dropped when their source tensor dies and the cache is next
+    consulted)."""
+    from . import distributed as gdist
+
+    _PACKED_ERI.clear()
+    gdist._PACKED_BLOCKS.clear()
+
+
+def _exchange_symmetric_blocked(sq: torch.Tensor, big: float, block: int = 4096) -> bool:
+    m = sq.shape[0]
+    worst = 0.0
+    for i in range(0, m, block):
+        for j in range(i, m, block):
+            worst = max(worst, float((sq[i:i + block, j:j + block] - sq[j:j + block, i:i + block].T).abs().max()))
+    return worst <= ERI_SYMMETRY_RTOL * big
+
+
+def coulomb_j_auto(P: torch.Tensor, eri: torch.Tensor) -> torch.Tensor:
+    """`coulomb_j` through the packed sweep when the tensor has one (see `packed_eri_for`), else the plain sweep.  What the
+    predictor and the `Molecule` methods call; `coulomb_j` itself always sweeps the tensor as given."""
+    pe = packed_eri_for(eri)
+    if pe is not None:
+        return _CoulombJPacked.apply(P, pe, eri)
+    return _CoulombJ.apply(P, eri)
 
 
 # ---------------------------------------------------------------------------------------------------------

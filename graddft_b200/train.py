@@ -165,7 +165,7 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
             n2 = atoms.rdm1.shape[-1] ** 2
             nv = int(bool(functional.densitygrads)) + int(bool(functional.coefficient_input_grads))
             # payload [V_xc | E_xc | J | V_HF...]: the density VJP's second-stage reduce writes V_xc straight into it
-            into = gdist.payload_segment(0, [2 * n2, 1] + ([n2] if shard.eri_row0 is not None else []) + [2 * n2] * nv, atoms.rdm1.device, shard.group)
+            into = gdist.payload_segment(0, [2 * n2, 1] + ([n2] if shard.eri_sharded else []) + [2 * n2] * nv, atoms.rdm1.device, shard.group)
         with ops.density_bwd_into(into):
             exc, fock_xc, at = xc_energy_and_grads(functional, params, atoms.rdm1, atoms, *args, create_graph=create_graph)
         differentiable = fock_xc.requires_grad
@@ -179,12 +179,12 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
             vterms = explicit_terms(params, at, False, *args)
             J = gdist.local_coulomb(P, atoms.rep_tensor, shard)
             (fock_xc, exc_sum, J, *vterms) = gdist.allreduce_sum_packed(
-                [fock_xc, exc.detach().reshape(1), J, *vterms], group=shard.group, skip=() if shard.eri_row0 is not None else (2,))
+                [fock_xc, exc.detach().reshape(1), J, *vterms], group=shard.group, skip=() if shard.eri_sharded else (2,))
             exc_sum = exc_sum.reshape(())
             exc = exc + (exc_sum - exc.detach()) if exc.requires_grad else exc_sum  # value: the global sum; gradient: identity
             EJ = (P * J).sum() / 2.0
         elif differentiable or atoms.rdm1.requires_grad:
-            J = ops.coulomb_j(P, atoms.rep_tensor)
+            J = ops.coulomb_j_auto(P, atoms.rep_tensor)
             EJ = (P * J).sum() / 2.0
         else:
             J, EJ = ops.coulomb_j_and_energy(P, atoms.rep_tensor)
@@ -214,7 +214,7 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
             exc = functional.energy_xc_only(params, atoms, *args, **kwargs)
         P = atoms.rdm1.sum(dim=0)
         if atoms.rdm1.requires_grad and torch.is_grad_enabled():
-            EJ = (P * ops.coulomb_j(P, atoms.rep_tensor)).sum() / 2.0
+            EJ = (P * ops.coulomb_j_auto(P, atoms.rep_tensor)).sum() / 2.0
         else:
             EJ = ops.coulomb_j_and_energy(P, atoms.rep_tensor)[1]
         return exc + (atoms.nuclear_repulsion + (P * atoms.h1e).sum() + EJ)
@@ -248,7 +248,7 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
                     exc = ops.xc_integrate(c, d, a.grid.weights, clip_cte)
                     P = a.rdm1.sum(dim=0)
                     if a.rdm1.requires_grad and torch.is_grad_enabled():
-                        EJ = (P * ops.coulomb_j(P, a.rep_tensor)).sum() / 2.0
+                        EJ = (P * ops.coulomb_j_auto(P, a.rep_tensor)).sum() / 2.0
                     else:
                         EJ = ops.coulomb_j_and_energy(P, a.rep_tensor)[1]
                     out[start + k] = exc + (a.nuclear_repulsion + (P * a.h1e).sum() + EJ)

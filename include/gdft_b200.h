@@ -152,6 +152,25 @@ int gdft_eri_j_rows(gdft_stream_t stream, int64_t n, int64_t rows, const double*
 int gdft_eri_j_transpose_rows(gdft_stream_t stream, int64_t n, int64_t rows, const double* eri_rows,
                               const double* Jbar_rows, double* Pbar, void* ws, size_t ws_bytes);
 
+/* ---- packed rep_tensor ("shard or pack").  (pq|rt) = (qp|rt) = (pq|tr), so
+ * J_pq = sum_{r>=t} (pq|rt) (P_rt + P_tr)(1 - delta_rt/2) needs the npair = n(n+1)/2 pair rows x pair columns only: a
+ * quarter of the 8 n^4 bytes of grad_dft/molecule.py:811's sweep, laid out once per molecule as
+ * packed[pair(p,q)][pair(r,t)], pair(i,j) = i(i+1)/2 + j (i >= j), row pitch = npair rounded up to even (padding 0).
+ * gdft_eri_symmetry_defect writes {max |asymmetry|, max |value|} over the given (p,q) rows (device, 2 doubles) so that the
+ * caller packs only tensors that ARE symmetric.  The packed matrix is symmetric, so the transpose of gdft_eri_j_packed
+ * (the VJP of J w.r.t. P) is gdft_eri_j_packed itself.  Pair rows shard like (p,q) rows: each rank sweeps
+ * [pair0, pair0 + pairs), writes zero elsewhere, and the Fock all-reduce assembles J. */
+int64_t gdft_eri_npair(int64_t n);
+size_t gdft_eri_packed_bytes(int64_t n, int64_t pairs);
+size_t gdft_eri_packed_workspace(int64_t n);
+int gdft_eri_symmetry_defect(gdft_stream_t stream, int64_t n, int64_t row0, int64_t rows, const double* eri_rows /*[rows,n,n]*/,
+                             double* out2 /*[2]*/, void* ws, size_t ws_bytes);
+int gdft_eri_pack(gdft_stream_t stream, int64_t n, int src_is_pair_rows, int64_t src_row0, int64_t src_rows,
+                  const double* src /*[src_rows,n,n]: (p,q) rows src_row0.., or exactly the pair rows pair0..*/,
+                  int64_t pair0, int64_t pairs, double* packed /*[pairs][npair_pad]*/);
+int gdft_eri_j_packed(gdft_stream_t stream, int64_t n, int64_t pair0, int64_t pairs, const double* packed,
+                      const double* P /*[n,n]*/, double* J /*[n,n]*/, double* EJ /*[1] or NULL*/, void* ws, size_t ws_bytes);
+
 /* ---- K6: XC quadrature ------------------------------------------------------------------------
  * E = sum_r aclip(w_r) aclip(aclip(sum_f c[r,f] d[r,f]))  (grad_dft/functional.py:251-253,342;
  * aclip = abs_clip, grad_dft/molecule.py:687-689).  c_rows is 1 (constant functionals,

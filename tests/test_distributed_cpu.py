@@ -188,3 +188,27 @@ def test_spin_split_fock_solver_gloo(world):
         assert torch.equal(w, res[0][1]) and torch.equal(C, res[0][2])      # replicated bit for bit
         assert torch.allclose(w, w0, rtol=0, atol=1e-13)
         assert torch.allclose(C.abs(), C0.abs(), rtol=0, atol=1e-10)        # eigenvector signs are the solver's choice
+
+
+def test_pair_row_sharding_partitions_the_lower_triangle():
+    """distributed.pair_bounds / pair_row_indices: the (p >= q) rows of a pair-symmetric rep_tensor, split evenly."""
+    from graddft_b200 import distributed as gdist
+
+    for n, world in ((7, 2), (43, 3), (264, 8)):
+        npair = n * (n + 1) // 2
+        seen = []
+        for r in range(world):
+            lo, hi = gdist.pair_bounds(n, r, world)
+            idx = gdist.pair_row_indices(n, lo, hi)
+            seen.append(idx)
+            assert hi - lo <= -(-npair // world) + 32
+        allrows = torch.cat(seen)
+        p, q = allrows // n, allrows % n
+        assert allrows.numel() == npair and bool((p >= q).all())
+        assert torch.equal(allrows, torch.sort(allrows).values) and allrows.unique().numel() == npair
+    mol = {"weights": torch.ones(256, dtype=torch.float64), "rep_tensor": torch.arange(5 ** 4, dtype=torch.float64).reshape(5, 5, 5, 5)}
+    part = gdist.shard_molecule_tensors(mol, 1, 2, shard_eri="pairs")
+    lo, hi = gdist.pair_bounds(5, 1, 2)
+    assert part["eri_pair0"] == lo and part["rep_tensor"].shape == (hi - lo, 5, 5)
+    rows = gdist.pair_row_indices(5, lo, hi)
+    assert torch.equal(part["rep_tensor"], mol["rep_tensor"].reshape(25, 5, 5)[rows])
