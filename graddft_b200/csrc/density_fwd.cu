@@ -24,7 +24,6 @@
 
 namespace gdft {
 
-constexpr int FWD_BM = 128;
 constexpr int FWD_BK = 12;
 constexpr int FWD_STAGES = 4;
 constexpr int FWD_THREADS = 256;
@@ -55,10 +54,12 @@ __global__ void transpose_pad_kernel(const double* __restrict__ D, double* __res
   }
 }
 
-template <int NTS>
-__global__ void __launch_bounds__(FWD_THREADS, 2)
+// MT = 8-row m-tiles per warp: 2 -> 128 grid rows per CTA, two CTAs per SM; 1 -> 64 rows per CTA, three CTAs per SM (finer
+// tiles: the last wave of CTAs wastes less, see use_64_rows).  The per-row arithmetic and its order are the same for both.
+template <int NTS, int MT>
+__global__ void __launch_bounds__(FWD_THREADS, MT == 2 ? 2 : 3)
 density_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
-  constexpr int BK = FWD_BK, BM = FWD_BM, STAGES = FWD_STAGES;
+  constexpr int BK = FWD_BK, BM = 64 * MT, STAGES = FWD_STAGES;
   constexpr int BN = 8 * NTS;                       // b-range per spin
   constexpr int STAGE_ELEMS = (BM + 2 * BN) * BK;   // doubles
   constexpr uint32_t STAGE_BYTES = STAGE_ELEMS * 8;
@@ -107,9 +108,9 @@ density_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   for (int pidx = 0; pidx < npass; pidx++) {
     const int aplane = pass0 ? pidx : pidx + 1;
     for (int ct = 0; ct < p.n_ctile; ct++) {
-      double acc[2][2 * NTS][2];
+      double acc[MT][2 * NTS][2];
 #pragma unroll
-      for (int i = 0; i < 2; i++)
+      for (int i = 0; i < MT; i++)
 #pragma unroll
         for (int j = 0; j < 2 * NTS; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -118,18 +119,20 @@ density_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&full[st], (it / STAGES) & 1);
         __syncthreads();  // every warp has finished iteration it-1, whose stage is refilled next
         if (tid == 0 && it + STAGES - 1 < total) issue(it + STAGES - 1);
-        const double* sA = sStage + st * STAGE_ELEMS + (warp * 16 + g) * BK + t;
+        const double* sA = sStage + st * STAGE_ELEMS + (warp * 8 * MT + g) * BK + t;
         const double* sB = sStage + st * STAGE_ELEMS + BM * BK + g * BK + t;
         const int ksteps = min(BK / 4, (npad - kt * BK) / 4);
 #pragma unroll
         for (int k4 = 0; k4 < BK / 4; k4++) {
           if (k4 < ksteps) {
-            const double a0 = sA[k4 * 4], a1 = sA[8 * BK + k4 * 4];
+            double a[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) a[mt] = sA[mt * 8 * BK + k4 * 4];
 #pragma unroll
             for (int j = 0; j < 2 * NTS; j++) {
               const double b = sB[j * 8 * BK + k4 * 4];
-              dmma884(acc[0][j], a0, b);
-              dmma884(acc[1][j], a1, b);
+#pragma unroll
+              for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][j], a[mt], b);
             }
           }
         }
@@ -138,8 +141,8 @@ density_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // ---- epilogue: contract the T tile against the planes (read once, shared by both spins) ----
       const int bcol0 = ct * BN + 2 * t;
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
-        const int rl = warp * 16 + mt * 8 + g;
+      for (int mt = 0; mt < MT; mt++) {
+        const int rl = warp * 8 * MT + mt * 8 + g;
         const int64_t row = row0 + rl;
         const bool rv = row < p.N;
         const double* prow = p.packed + (size_t)row * npad + bcol0;
@@ -229,19 +232,37 @@ static int pick_nts(int nsub) {
   return best;
 }
 
-template <int NTS>
-static int launch_fwd(cudaStream_t stream, const CUtensorMap& tmA, const double* DT, FwdParams p) {
-  CUtensorMap tmB;
-  int rc = make_tmap_3d(&tmB, DT, p.npad, p.npad, 2, (uint64_t)p.npad * 8, (uint64_t)p.npad * p.npad * 8, FWD_BK, 8 * NTS);
+template <int NTS, int MT>
+static int launch_fwd_mt(cudaStream_t stream, const double* DT, FwdParams p) {
+  constexpr int BM = 64 * MT;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_3d(&tmA, p.packed, p.npad, (uint64_t)p.N, p.nplanes, (uint64_t)p.npad * 8, (uint64_t)p.N * p.npad * 8, FWD_BK, BM);
+  if (rc) return rc;
+  rc = make_tmap_3d(&tmB, DT, p.npad, p.npad, 2, (uint64_t)p.npad * 8, (uint64_t)p.npad * p.npad * 8, FWD_BK, 8 * NTS);
   if (rc) return rc;
   p.n_ctile = (p.npad / 8 + NTS - 1) / NTS;
   p.n_ktile = (p.npad + FWD_BK - 1) / FWD_BK;
-  size_t smem = (size_t)FWD_STAGES * (FWD_BM + 16 * NTS) * FWD_BK * 8 + (size_t)p.nslots * FWD_BM * 8 + FWD_STAGES * 8;
-  GDFT_CUDA_TRY(cudaFuncSetAttribute(density_fwd_kernel<NTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  unsigned grid = (unsigned)((p.N + FWD_BM - 1) / FWD_BM);
-  density_fwd_kernel<NTS><<<grid, FWD_THREADS, smem, stream>>>(tmA, tmB, p);
+  size_t smem = (size_t)FWD_STAGES * (BM + 16 * NTS) * FWD_BK * 8 + (size_t)p.nslots * BM * 8 + FWD_STAGES * 8;
+  GDFT_CUDA_TRY(cudaFuncSetAttribute(density_fwd_kernel<NTS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  unsigned grid = (unsigned)((p.N + BM - 1) / BM);
+  density_fwd_kernel<NTS, MT><<<grid, FWD_THREADS, smem, stream>>>(tmA, tmB, p);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
+}
+
+// 64-row CTAs (three per SM) for the tensor-pipe-bound widths: measured on B200 (tools/rows_probe.py) they match or beat
+// the 128-row shape from n = 264 up at every grid size (62 500 rows, the per-GPU share of the benzene shape on 8 GPUs:
+// 2.74 -> 2.46 ms, because 489 128-row tiles fill 296 slots 1.65 times and cost two full waves; 500 000 rows: 17.65 -> 17.51
+// ms; n = 400, 250 000 rows: 19.88 -> 19.66 ms).  Narrow matrices (n = 100, 40 000 rows: 0.49 -> 0.57 ms) are bound by the
+// per-CTA chain of TMA round trips and epilogue loads, which the smaller tile lengthens: they keep 128 rows.
+static bool use_64_rows(int64_t N, int npad) {
+  if (const char* e = getenv("GDFT_FWD_ROWS")) { int v = atoi(e); if (v == 64) return true; if (v == 128) return false; }
+  return npad >= 192 && (N + 127) / 128 > 2 * 148;
+}
+
+template <int NTS>
+static int launch_fwd(cudaStream_t stream, const double* DT, FwdParams p) {
+  return use_64_rows(p.N, p.npad) ? launch_fwd_mt<NTS, 1>(stream, DT, p) : launch_fwd_mt<NTS, 2>(stream, DT, p);
 }
 
 size_t density_fwd_workspace(int64_t n) {
@@ -280,20 +301,16 @@ extern "C" int gdft_density_fwd(gdft_stream_t stream_, int64_t N, int64_t n, int
     transpose_pad_kernel<<<grd, blk, 0, stream>>>(rdm1, DT, (int)n, npad);
     GDFT_LAUNCH_CHECK();
   }
-  CUtensorMap tmA;
-  int rc = make_tmap_3d(&tmA, packed, npad, (uint64_t)N, nplanes, (uint64_t)npad * 8, (uint64_t)N * npad * 8, FWD_BK, FWD_BM);
-  if (rc) return rc;
-
   FwdParams p{};
   p.N = N; p.n = (int)n; p.npad = npad; p.nplanes = nplanes; p.flags = flags; p.W = (flags & GDFT_HF) ? W : 0;
   p.nslots = FWD_SLOT_HF + 2 * p.W;
   p.packed = packed; p.chi = chi_packed;
   p.rho = rho; p.grho = grad_rho; p.tau = tau; p.lapl = lapl; p.ehf = ehf;
   switch (pick_nts(npad / 8)) {
-    case 1: return launch_fwd<1>(stream, tmA, DT, p);
-    case 2: return launch_fwd<2>(stream, tmA, DT, p);
-    case 3: return launch_fwd<3>(stream, tmA, DT, p);
-    case 4: return launch_fwd<4>(stream, tmA, DT, p);
-    default: return launch_fwd<5>(stream, tmA, DT, p);
+    case 1: return launch_fwd<1>(stream, DT, p);
+    case 2: return launch_fwd<2>(stream, DT, p);
+    case 3: return launch_fwd<3>(stream, DT, p);
+    case 4: return launch_fwd<4>(stream, DT, p);
+    default: return launch_fwd<5>(stream, DT, p);
   }
 }

@@ -114,3 +114,20 @@ def test_second_order_closure(cuda_device):
     (hvc,) = torch.autograd.grad((g1c * v).sum(), Dc)
     assert relerr(g1.detach(), g1c.detach()) < RTOL
     assert relerr(hv, hvc) < RTOL
+
+
+@pytest.mark.parametrize("N,n,seed", [(1000, 12, 1984), (777, 43, 1993), (1500, 264, 1993), (1300, 400, 1984), (513, 7, 1993)])
+def test_density_forward_row_tile_shapes_agree_bitwise(cuda_device, N, n, seed, monkeypatch):
+    """K1's 64-row CTA shape (mid-size grids) against its 128-row shape: the per-row summation order does not depend on
+    the tile height, so every output is bitwise the same -- and both match the oracle."""
+    mol, basis = make(N, n, seed, cuda_device)
+    D = mol["rdm1"].to(cuda_device)
+    flags = GDFT_RHO | GDFT_GRAD | GDFT_TAU | GDFT_LAPL | GDFT_HF
+    monkeypatch.setenv("GDFT_FWD_ROWS", "128")
+    ref = ops._density_fwd_raw(basis, D, flags)
+    monkeypatch.setenv("GDFT_FWD_ROWS", "64")
+    got = ops._density_fwd_raw(basis, D, flags)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    assert relerr(got[0], oracle.density(mol["rdm1"], mol["ao"])) < RTOL
+    assert relerr(got[2], oracle.kinetic_density(mol["rdm1"], mol["grad_ao"])) < RTOL
