@@ -308,10 +308,34 @@ def diff_scf_loop(functional: Functional, cycles: int = 25, **kwargs) -> Callabl
             z = torch.zeros((diis.max_diis, 2, n, n), dtype=A.dtype, device=A.device)
             return (z, z.clone(), torch.zeros(diis.max_diis, dtype=A.dtype, device=A.device), z.clone())
 
-        diis_data = fresh()
         norm_gorb = None
         L_inv = overlap_factor(molecule.s1e)  # loop-invariant
         warm = {}  # eigenvectors of the previous cycle (Jacobi warm start)
+        from .train import _requires_grad
+        no_grad = not (torch.is_grad_enabled() and (_requires_grad(params) or molecule.rdm1.requires_grad))
+        if no_grad and ops.scf_stage_supported(molecule.rdm1, diis.max_diis) and molecule.s1e.dim() == 2:
+            # small molecules: the whole n x n tail of an iteration is two kernels around the eigensolver
+            # (gdft_scf_diis_step, gdft_scf_occupy) instead of ~55 host-framework launches; ring buffers rotate in place
+            m_ = diis.max_diis
+            fock_vec = torch.zeros((m_, 2, n, n), dtype=A.dtype, device=A.device)
+            err_vec = torch.zeros_like(fock_vec)
+            gram = torch.zeros((2, m_, m_), dtype=A.dtype, device=A.device)
+            for cycle in range(cycles):
+                C, fock_diis, _ = ops.scf_diis_step(cycle, molecule.fock, molecule.rdm1, molecule.s1e, L_inv, fock_vec, err_vec, gram)
+                uses = warm.get("uses", 0)
+                cold = uses % WARM_RESTART_EVERY == 0  # V_k = V_{k-1} V'_k drifts from orthogonality: a cold start every few cycles
+                mo_energy, evecs_t = ops.sym_eigh(C, None if cold else warm.get("V"), warm.get("info"))
+                warm["V"], warm["uses"] = evecs_t, uses + 1
+                mo_coeff, mo_occ, rdm1 = ops.scf_occupy(mo_energy, evecs_t, L_inv, molecule.mo_occ)
+                molecule = molecule.replace(fock=fock_diis, mo_coeff=mo_coeff, mo_energy=mo_energy, mo_occ=mo_occ, rdm1=rdm1)
+                predicted_e, fock = compute_energy(params, molecule, *args)
+                molecule = molecule.replace(fock=fock)
+            # the orbital gradient norm is loop state upstream (evaluate.py:1016) but only its last value is ever read
+            norm_gorb = torch.linalg.norm(molecule.get_mo_grads()) if cycles > 0 else None
+            molecule = molecule.replace(energy=predicted_e)
+            object.__setattr__(molecule, "_norm_gorb", norm_gorb)
+            return molecule
+        diis_data = fresh()
         for cycle in range(cycles):
             fock, diis_data = diis.run((molecule.rdm1, molecule.fock, predicted_e), diis_data, cycle)
             molecule, predicted_e = _scf_body(compute_energy, params, molecule, fock, *args, L_inv=L_inv, warm=warm)

@@ -992,6 +992,40 @@ def sym_eigh(A: torch.Tensor, V0: Optional[torch.Tensor] = None, info: Optional[
     return evals, evecs
 
 
+# ---------------------------------------------------------------------------------------------------------
+# SCF harness: the n x n tail of a DIIS iteration of a small molecule as two kernels (row f1)
+# ---------------------------------------------------------------------------------------------------------
+def scf_stage_supported(t: torch.Tensor, max_diis: int) -> bool:
+    import os
+
+    if os.environ.get("GDFT_SCF_FUSED", "1") == "0":  # A/B switch: the host-framework tail
+        return False
+    return t.is_cuda and t.dtype == F64 and t.shape[-1] <= lib().gdft_scf_stage_max_n() and max_diis <= 16
+
+
+def scf_diis_step(cycle: int, fock, rdm1, overlap, L_inv, fock_vec, err_vec, gram):
+    """One CDIIS step of grad_dft/evaluate.py:1111-1205 on the loop-private ring buffers (updated in place) followed by the
+    Cholesky reduction of eigenproblem.py:125-127: returns (C = L^-1 F' L^-T, F', x) -- see gdft_scf_diis_step."""
+    n, m = int(fock.shape[-1]), int(fock_vec.shape[0])
+    fock, rdm1, overlap, L_inv = _c(fock.detach()), _c(rdm1.detach()), _c(overlap.detach()), _c(L_inv.detach())
+    C = torch.empty_like(fock)
+    fock_out = torch.empty_like(fock)
+    x = torch.empty((2, m), dtype=F64, device=fock.device)
+    check(lib().gdft_scf_diis_step(stream_ptr(), n, m, int(cycle), ptr(fock), ptr(rdm1), ptr(overlap), ptr(L_inv), ptr(fock_vec), ptr(err_vec),
+                                   ptr(gram), ptr(x), ptr(fock_out), ptr(C)), "gdft_scf_diis_step")
+    return C, fock_out, x
+
+
+def scf_occupy(evals, V, L_inv, occ_prev):
+    """(mo_coeff = L^-T V, aufbau occupations, rdm1 = C occ C^T) -- eigenproblem.py:129, molecule.py:815-889."""
+    n = int(V.shape[-1])
+    evals, V, L_inv, occ_prev = _c(evals.detach()), _c(V.detach()), _c(L_inv.detach()), _c(occ_prev.detach())
+    mo_coeff, rdm1 = torch.empty_like(V), torch.empty_like(V)
+    mo_occ = torch.empty_like(evals)
+    check(lib().gdft_scf_occupy(stream_ptr(), n, ptr(evals), ptr(V), ptr(L_inv), ptr(occ_prev), ptr(mo_coeff), ptr(mo_occ), ptr(rdm1)), "gdft_scf_occupy")
+    return mo_coeff, mo_occ, rdm1
+
+
 class _AbsClip(Function):
     """out = where(|src| > thr, x, 0): abs_clip for x = src, and the same mask applied to a cotangent in its VJP (which is
     again this Function, so any order of differentiation closes over the one kernel).  No gradient flows to `src`."""

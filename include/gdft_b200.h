@@ -292,6 +292,23 @@ int gdft_diis_matrix(gdft_stream_t stream, int m, int64_t n, int cycle, const do
 int gdft_diis_combine(gdft_stream_t stream, int m, int64_t n, const double* x /*[2,m]*/, const double* fock_vec,
                       double* out /*[2,n,n]*/);
 
+/* The n x n tail of one DIIS SCF iteration of a small molecule (n <= gdft_scf_stage_max_n() = 64, max_diis <= 16) as two
+ * kernels around the eigensolver, one CTA per spin, no host-visible status (graph-capturable):
+ * gdft_scf_diis_step: err = FDS - (FDS)^T, ring-buffer slot written in place (logical entry i lives in physical slot
+ *   (head + i) % m, head = max(0, cycle - m) % m: the slot rotates where upstream shifts the whole buffer; cycle == m is
+ *   dropped like upstream's out-of-bounds .at[].set()), the one new row/column of the persistent Gram matrix, the bordered
+ *   CDIIS matrix, x = B^-1 e_0 (LU with partial pivoting), F' = sum_i x_i F_i, and the reduced matrix C = L^-1 F' L^-T
+ *   (grad_dft/evaluate.py:1111-1205, grad_dft/utils/eigenproblem.py:125-127).
+ * gdft_scf_occupy: mo_coeff = L^-T V, aufbau occupations by stable rank with nelec = round(sum occ_prev), rdm1 = C occ C^T
+ *   (eigenproblem.py:129, grad_dft/molecule.py:815-889). */
+int gdft_scf_stage_max_n(void);
+int gdft_scf_diis_step(gdft_stream_t stream, int64_t n, int m, int cycle, const double* fock /*[2,n,n]*/, const double* rdm1 /*[2,n,n]*/,
+                       const double* overlap /*[n,n]*/, const double* L_inv /*[n,n]*/, double* fock_vec /*[m,2,n,n]*/,
+                       double* err_vec /*[m,2,n,n]*/, double* gram /*[2,m,m]*/, double* x_out /*[2,m]*/, double* fock_out /*[2,n,n]*/,
+                       double* C_out /*[2,n,n]*/);
+int gdft_scf_occupy(gdft_stream_t stream, int64_t n, const double* evals /*[2,n]*/, const double* V /*[2,n,n]*/, const double* L_inv,
+                    const double* occ_prev /*[2,n]*/, double* mo_coeff /*[2,n,n]*/, double* mo_occ /*[2,n]*/, double* rdm1 /*[2,n,n]*/);
+
 /* abs_clip (grad_dft/molecule.py:687-689) and its VJP in one elementwise pass: out[i] = |src[i]| > thr ? x[i] : 0
  * (x = src: the clip; x = a cotangent: the cotangent of the clip's input).  NaN in src gives 0, as jnp.where does. */
 int gdft_abs_clip(gdft_stream_t stream, int64_t count, const double* x, const double* src, double thr, double* out);
