@@ -1071,7 +1071,8 @@ def chi_leg(ctx):
         ms_e = ctx.timed(e2e, 3) / 3
         out["e2e"] = {"value": host_rows / (ms_e / 1e3), "unit": "points/s", "h2d_bytes_per_step": 8 * host_rows * n * n,
                       "d2h_bytes_per_step": 0, "ms_per_step": ms_e, "h2d_GBps": 8e-6 * host_rows * n * n / ms_e,
-                      "note": "nu chunks of 1024 points from pageable host memory through two pinned buffers"}
+                      "note": "nu chunks of 1024 points from pageable host memory, staged into two cached page-locked buffers by a pool of host threads, "
+                              "each row slice uploaded as soon as it is staged"}
         nu_pinned = nu_host.pin_memory()
 
         def e2e_pinned():
