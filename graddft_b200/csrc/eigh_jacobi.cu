@@ -249,6 +249,32 @@ __device__ __forceinline__ void eig_pair_rotation(const double* __restrict__ src
   }
 }
 
+// n x n products of the warm start as FP64 tensor tiles (one 8 x 8 tile per warp and round, predicated fragment loads, so
+// neither padding nor alignment is asked of the operands): C(i,j) = sum_k opA(i,k) opB(k,j).  As scalar loops the three
+// products of a warm start were shared-memory-bandwidth-bound (two 8-byte loads per FMA, n^3 / 8 wavefronts: ~5 us each at
+// n = 43, a fifth of the whole solve).  `out(i, j, value)` receives every element with i, j < n.
+template <bool TA, bool TB, typename Out>
+__device__ __forceinline__ void eig_mma(int n, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, Out out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nt = (n + 7) >> 3;
+  for (int tile = warp; tile < nt * nt; tile += EIG_THREADS / 32) {
+    const int i = ((tile / nt) << 3) + g, j = ((tile % nt) << 3) + g;
+    double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+    for (int k0 = 0; k0 < n; k0 += 8) {
+      const int ka = k0 + t, kb = k0 + 4 + t;
+      const double a0 = (i < n && ka < n) ? (TA ? A[ka * lda + i] : A[i * lda + ka]) : 0.0;
+      const double a1 = (i < n && kb < n) ? (TA ? A[kb * lda + i] : A[i * lda + kb]) : 0.0;
+      const double b0 = (j < n && ka < n) ? (TB ? B[j * ldb + ka] : B[ka * ldb + j]) : 0.0;
+      const double b1 = (j < n && kb < n) ? (TB ? B[j * ldb + kb] : B[kb * ldb + j]) : 0.0;
+      dmma884(c0, a0, b0);
+      dmma884(c1, a1, b1);
+    }
+    const int jc = ((tile % nt) << 3) + 2 * t;
+    if (i < n && jc < n) out(i, jc, c0[0] + c1[0]);
+    if (i < n && jc + 1 < n) out(i, jc + 1, c0[1] + c1[1]);
+  }
+}
+
 template <int NB, int NR>
 __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n, const double* __restrict__ A_in, const double* __restrict__ V0_in,
                                                                            double* __restrict__ evals, double* __restrict__ evecs,
@@ -281,21 +307,28 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
     double* sT = sA + (size_t)m * m;  // the second copy of A as scratch: T = A V0, [n][m]
     for (int idx = tid; idx < n * n; idx += EIG_THREADS) sV0[idx] = V0[idx];
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += EIG_THREADS) {
-      const int i = idx / n, j = idx - i * n;
-      double acc = 0.0;
-      for (int k = 0; k < n; k++) acc = fma(sA[i * m + k], sV0[k * n + j], acc);
-      sT[i * m + j] = acc;
-    }
+    // V0 is handed from cycle to cycle as V0 V', which drifts from orthogonality by a few ulps per cycle: one Newton-Schulz
+    // step V0 <- V0 + 1/2 V0 (I - V0^T V0) squares the defect away (1e-13 -> 1e-26), so no periodic cold start is needed
+    eig_mma<true, false>(n, sV0, n, sV0, n, [&](int i, int j, double v) { sT[i * m + j] = (i == j ? 1.0 : 0.0) - v; });
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += EIG_THREADS) {  // A' = V0^T T (only its upper triangle is used below)
-      const int i = idx / n, j = idx - i * n;
-      if (i <= j) {
-        double acc = 0.0;
-        for (int k = 0; k < n; k++) acc = fma(sV0[k * n + i], sT[k * m + j], acc);
-        sA[i * m + j] = acc;
+    {
+      constexpr int MAXT = (64 / 8) * (64 / 8) / (EIG_THREADS / 32);  // tiles per warp at n = 64
+      double corr[2 * MAXT];
+      int cnt = 0;
+      eig_mma<false, false>(n, sV0, n, sT, m, [&](int, int, double v) { if (cnt < 2 * MAXT) corr[cnt] = v; cnt++; });
+      __syncthreads();
+      cnt = 0;
+      const int nt = (n + 7) >> 3, g = lane >> 2, t = lane & 3;
+      for (int tile = warp; tile < nt * nt; tile += EIG_THREADS / 32) {  // the same walk as eig_mma's, same order of emission
+        const int i = ((tile / nt) << 3) + g, jc = ((tile % nt) << 3) + 2 * t;
+        if (i < n && jc < n) { sV0[i * n + jc] = fma(0.5, corr[cnt], sV0[i * n + jc]); cnt++; }
+        if (i < n && jc + 1 < n) { sV0[i * n + jc + 1] = fma(0.5, corr[cnt], sV0[i * n + jc + 1]); cnt++; }
       }
     }
+    __syncthreads();
+    eig_mma<false, false>(n, sA, m, sV0, n, [&](int i, int j, double v) { sT[i * m + j] = v; });  // T = A V0
+    __syncthreads();
+    eig_mma<true, false>(n, sV0, n, sT, m, [&](int i, int j, double v) { if (i <= j) sA[i * m + j] = v; });  // A' = V0^T T (upper triangle)
   }
   // V rows: row i = (warp - NAW) + NVW * q, lane l holds the position pair (2l, 2l+1); rows >= n stay zero
   double vt[NR], vb[NR];
@@ -457,12 +490,7 @@ __global__ void __launch_bounds__(EIG_THREADS) sym_eig_jacobi_small_kernel(int n
   }
   if (warm) {
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += EIG_THREADS) {  // V = V0 V'
-      const int i = idx / n, j = idx - i * n;
-      double acc = 0.0;
-      for (int k = 0; k < n; k++) acc = fma(sV0[i * n + k], sVp[k * n + j], acc);
-      vec[idx] = acc;
-    }
+    eig_mma<false, false>(n, sV0, n, sVp, n, [&](int i, int j, double v) { vec[(size_t)i * n + j] = v; });  // V = V0 V'
   }
 }
 

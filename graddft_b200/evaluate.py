@@ -138,7 +138,6 @@ def refine_eigh(C: Array, X: Array) -> Tuple[Optional[Array], Optional[Array]]:
     return None, None
 
 
-WARM_RESTART_EVERY = 8  # cold Jacobi start every so many cycles: V_k = V_{k-1} V'_k accumulates round-off in its orthogonality
 
 
 def safe_general_eigh(A: Array, B: Array, L_inv: Optional[Array] = None, shard=None, warm: Optional[dict] = None) -> Tuple[Array, Array]:
@@ -149,12 +148,10 @@ def safe_general_eigh(A: Array, B: Array, L_inv: Optional[Array] = None, shard=N
         L_inv = overlap_factor(B)
     C = L_inv @ A @ L_inv.transpose(-1, -2)
     if (warm is not None and ops.sym_eigh_supported(C) and not (torch.is_grad_enabled() and C.requires_grad)):
-        uses = warm.get("uses", 0)
-        # n <= 64 returns V0 V', whose orthogonality drifts: a cold start every few cycles; the cluster kernel (n > 64)
-        # re-derives its eigenvectors from (C + sigma I) V0 every time and needs none
-        cold = C.shape[-1] <= 64 and uses % WARM_RESTART_EVERY == 0
-        evals, evecs_t = ops.sym_eigh(C, None if cold else warm.get("V"), warm.get("info"))
-        warm["V"], warm["uses"] = evecs_t, uses + 1
+        # n <= 64 returns V0 V'; the kernel re-orthogonalises V0 (one Newton-Schulz step) before using it, so the product
+        # does not drift; the cluster kernel (n > 64) re-derives its eigenvectors from (C + sigma I) V0 every time
+        evals, evecs_t = ops.sym_eigh(C, warm.get("V"), warm.get("info"))
+        warm["V"] = evecs_t
         return evals, L_inv.transpose(-1, -2) @ evecs_t
     no_grad = not (torch.is_grad_enabled() and C.requires_grad)
     if warm is not None and no_grad and C.is_cuda and shard is None and not ops.sym_eigh_supported(C):
@@ -322,10 +319,8 @@ def diff_scf_loop(functional: Functional, cycles: int = 25, **kwargs) -> Callabl
             gram = torch.zeros((2, m_, m_), dtype=A.dtype, device=A.device)
             for cycle in range(cycles):
                 C, fock_diis, _ = ops.scf_diis_step(cycle, molecule.fock, molecule.rdm1, molecule.s1e, L_inv, fock_vec, err_vec, gram)
-                uses = warm.get("uses", 0)
-                cold = uses % WARM_RESTART_EVERY == 0  # V_k = V_{k-1} V'_k drifts from orthogonality: a cold start every few cycles
-                mo_energy, evecs_t = ops.sym_eigh(C, None if cold else warm.get("V"), warm.get("info"))
-                warm["V"], warm["uses"] = evecs_t, uses + 1
+                mo_energy, evecs_t = ops.sym_eigh(C, warm.get("V"), warm.get("info"))  # warm start from the previous cycle
+                warm["V"] = evecs_t
                 mo_coeff, mo_occ, rdm1 = ops.scf_occupy(mo_energy, evecs_t, L_inv, molecule.mo_occ)
                 molecule = molecule.replace(fock=fock_diis, mo_coeff=mo_coeff, mo_energy=mo_energy, mo_occ=mo_occ, rdm1=rdm1)
                 predicted_e, fock = compute_energy(params, molecule, *args)

@@ -480,3 +480,27 @@ def test_sym_eigh_status_word_small(cuda_device):
     A[1, 0, 0] = float("inf")
     ops.sym_eigh(A, info=info)
     assert int(info[1]) == -2 and int(info[0]) >= 1
+
+
+@pytest.mark.parametrize("n", [13, 43, 64])
+def test_sym_eigh_warm_start_reorthogonalises_its_start(cuda_device, n):
+    """The one-CTA Jacobi kernel returns V0 V'; chained over many SCF cycles the product would drift from orthogonality.
+    The kernel applies one Newton-Schulz step to V0 first: a start that is orthogonal only to 1e-8 still yields an
+    orthogonal decomposition, and a 200-cycle chain stays at working accuracy (no periodic cold start)."""
+    g = torch.Generator().manual_seed(n)
+    A = torch.randn(2, n, n, generator=g, dtype=torch.float64)
+    A = (A + A.transpose(1, 2)).to(cuda_device)
+    eye = torch.eye(n, dtype=torch.float64, device=cuda_device)
+    _, V = ops.sym_eigh(A)
+    V_bad = V + 1e-8 * torch.randn(V.shape, generator=g, dtype=torch.float64).to(cuda_device)  # defect 1e-7: one step leaves its square
+    w, V2 = ops.sym_eigh(A, V_bad)
+    assert float((V2.transpose(1, 2) @ V2 - eye).abs().max()) < 1e-12
+    assert float((V2.transpose(1, 2) @ A @ V2 - torch.diag_embed(w)).abs().max()) < 1e-11 * float(A.abs().max()) * n
+    Vk = V
+    for k in range(200):
+        P = torch.randn(2, n, n, generator=g, dtype=torch.float64).to(cuda_device)
+        Ak = A + 1e-3 * (P + P.transpose(1, 2))
+        wk, Vk = ops.sym_eigh(Ak, Vk)
+    assert float((Vk.transpose(1, 2) @ Vk - eye).abs().max()) < 1e-13 * n
+    w_ref = torch.linalg.eigvalsh(Ak)
+    assert float((wk - w_ref).abs().max()) < 1e-11 * float(A.abs().max()) * n
