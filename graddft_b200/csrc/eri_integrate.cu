@@ -124,6 +124,23 @@ __global__ void __launch_bounds__(1024) dot_kernel(int64_t n, const double* __re
   }
 }
 
+// out[0] = E_nuc + sum_i P[i] (h[i] + J[i] / 2): the non-XC energy of grad_dft/molecule.py:697-733 (E_nuc + E_1 + E_J) from the
+// spin-summed density matrix, the core Hamiltonian and the Coulomb matrix in one pass (single CTA, fixed order)
+__global__ void __launch_bounds__(1024) nonxc_energy_kernel(int64_t n, const double* __restrict__ P, const double* __restrict__ h,
+                                                           const double* __restrict__ J, const double* __restrict__ enuc, double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc = fma(P[i], fma(0.5, J[i], h[i]), acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = red[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = enuc[0] + v;
+  }
+}
+
 // K[p][r] += sum_t eri[p][q][r][t] P[q][t]  for all q: one CTA per (p, r-block); not in the reference
 //  -- same ERI stream with the other index pairing.
 __global__ void __launch_bounds__(256) eri_k_kernel(int n, const double* __restrict__ eri, const double* __restrict__ P,
@@ -380,6 +397,15 @@ static int eri_gemv_launch(cudaStream_t stream, int64_t C, int64_t rows, const d
     if (vec) eri_j_kernel<true, 4><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
     else eri_j_kernel<false, 4><<<grid, ERI_THREADS, 0, stream>>>(rows, C, eri_rows, P, J_rows);
   }
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
+}
+
+extern "C" int gdft_nonxc_energy(gdft_stream_t stream, int64_t n, const double* P, const double* h1e, const double* J,
+                                 const double* nuclear_repulsion, double* out) {
+  if (n <= 0 || n > 32768) return GDFT_BAD_SHAPE;
+  if (!P || !h1e || !J || !nuclear_repulsion || !out) return GDFT_BAD_ARGUMENT;
+  nonxc_energy_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(n * n, P, h1e, J, nuclear_repulsion, out);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }

@@ -375,6 +375,11 @@ class Molecule:
                 and coefficient_inputs is b.cinputs and densities_wout_hf is b.grad_densities):
             # the coefficients of this very (params, coefficient_inputs) pair were evaluated by the XC build of the same
             # predictor call: molecule.py:600-604 with them as constants (no second pass through the network)
+            if b.g_densities is not None:
+                # ... and dE_xc/d e_HF through the densities is the cotangent that reached the stop_gradient boundary in that
+                # build's own backward pass (its densities are abs_clip'ed, a difference of at most 1e-30 in magnitude --
+                # DESIGN.md section 4): no second quadrature pass either
+                return ops.hf_fock(basis, b.g_densities)
             ehf_leaf = ehf.detach().requires_grad_(True)
             with torch.enable_grad():
                 e = ops.xc_integrate(b.coefficients, functional.combine_densities(densities_wout_hf, ehf_leaf), self.grid.weights, 1e-30)

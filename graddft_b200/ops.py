@@ -380,6 +380,18 @@ def coulomb_j_and_energy(P: torch.Tensor, eri: torch.Tensor) -> Tuple[torch.Tens
     return J, EJ[0]
 
 
+def nonxc_energy(P: torch.Tensor, h1e: torch.Tensor, J: torch.Tensor, nuclear_repulsion) -> torch.Tensor:
+    """E_nuc + <P, h1e> + 1/2 <P, J> (grad_dft/molecule.py:697-733) as one kernel; no autograd (the predictor's first-order path)."""
+    P, h1e, J = _c(P.detach()), _c(h1e.detach()), _c(J.detach())
+    n = int(P.shape[0])
+    if not isinstance(nuclear_repulsion, torch.Tensor):
+        nuclear_repulsion = torch.tensor(float(nuclear_repulsion), dtype=F64, device=P.device)
+    en = _c(nuclear_repulsion.detach().reshape(1).to(P.device))
+    out = torch.empty((1,), dtype=F64, device=P.device)
+    check(lib().gdft_nonxc_energy(stream_ptr(), n, ptr(P), ptr(h1e), ptr(J), ptr(en), ptr(out)), "gdft_nonxc_energy")
+    return out[0]
+
+
 # ---------------------------------------------------------------------------------------------------------
 # packed rep_tensor: the pair-symmetric quarter of the ERI sweep, laid out once per molecule (like the packed basis)
 # ---------------------------------------------------------------------------------------------------------

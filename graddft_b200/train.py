@@ -182,13 +182,14 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
                 [fock_xc, exc.detach().reshape(1), J, *vterms], group=shard.group, skip=() if shard.eri_sharded else (2,))
             exc_sum = exc_sum.reshape(())
             exc = exc + (exc_sum - exc.detach()) if exc.requires_grad else exc_sum  # value: the global sum; gradient: identity
-            EJ = (P * J).sum() / 2.0
         elif differentiable or atoms.rdm1.requires_grad:
             J = ops.coulomb_j_auto(P, atoms.rep_tensor)
-            EJ = (P * J).sum() / 2.0
         else:
-            J, EJ = ops.coulomb_j_and_energy(P, atoms.rep_tensor)
-        energy = exc + (atoms.nuclear_repulsion + (P * atoms.h1e).sum() + EJ)  # train.py:150, molecule.py:727-733
+            J = ops.coulomb_j_auto(P.detach(), atoms.rep_tensor)
+        if P.is_cuda and not (J.requires_grad or P.requires_grad):
+            energy = exc + ops.nonxc_energy(P, atoms.h1e, J, atoms.nuclear_repulsion)  # train.py:150, molecule.py:727-733 in one kernel
+        else:
+            energy = exc + (atoms.nuclear_repulsion + (P * atoms.h1e).sum() + (P * J).sum() / 2.0)  # train.py:150, molecule.py:727-733
 
         if fock_xc.requires_grad or J.requires_grad:
             fock = atoms.h1e + J + fock_xc

@@ -152,6 +152,11 @@ int gdft_eri_j_rows(gdft_stream_t stream, int64_t n, int64_t rows, const double*
 int gdft_eri_j_transpose_rows(gdft_stream_t stream, int64_t n, int64_t rows, const double* eri_rows,
                               const double* Jbar_rows, double* Pbar, void* ws, size_t ws_bytes);
 
+/* E_nuc + E_1 + E_J = nuclear_repulsion + <P, h1e> + 1/2 <P, J> (grad_dft/molecule.py:697-733, 738-783) in one pass over the
+ * n x n matrices; nuclear_repulsion and out are device scalars. */
+int gdft_nonxc_energy(gdft_stream_t stream, int64_t n, const double* P /*[n,n]*/, const double* h1e, const double* J,
+                      const double* nuclear_repulsion /*[1]*/, double* out /*[1]*/);
+
 /* ---- packed rep_tensor ("shard or pack").  (pq|rt) = (qp|rt) = (pq|tr), so
  * J_pq = sum_{r>=t} (pq|rt) (P_rt + P_tr)(1 - delta_rt/2) needs the npair = n(n+1)/2 pair rows x pair columns only: a
  * quarter of the 8 n^4 bytes of grad_dft/molecule.py:811's sweep, laid out once per molecule as
