@@ -15,8 +15,9 @@
  *   - every call is stream-ordered on `stream` (a cudaStream_t), never synchronises the device,
  *     never allocates: scratch comes from the caller's `ws` (size from gdft_workspace_bytes);
  *   - return value: 0 OK, 1 bad shape, 2 bad alignment, 3 workspace too small, 4 CUDA error
- *     (code via gdft_last_cuda_error(), thread-local), 5 bad argument.  No exceptions, no global
- *     mutable state: safe to call from any host thread on any stream/device;
+ *     (code via gdft_last_cuda_error(), thread-local), 5 bad argument.  No exceptions; the only
+ *     process-wide state is a relaxed atomic launch counter (statistics, gdft_launch_count) and the
+ *     lazily resolved libnccl entry points: safe to call from any host thread on any stream/device;
  *   - there is NO CPU implementation in this library.
  */
 #ifndef GDFT_B200_H
