@@ -186,7 +186,8 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
             J = ops.coulomb_j_auto(P, atoms.rep_tensor)
         else:
             J = ops.coulomb_j_auto(P.detach(), atoms.rep_tensor)
-        if P.is_cuda and not (J.requires_grad or P.requires_grad):
+        enuc = atoms.nuclear_repulsion
+        if P.is_cuda and isinstance(enuc, torch.Tensor) and enuc.is_cuda and not (J.requires_grad or P.requires_grad or enuc.requires_grad):
             energy = exc + ops.nonxc_energy(P, atoms.h1e, J, atoms.nuclear_repulsion)  # train.py:150, molecule.py:727-733 in one kernel
         else:
             energy = exc + (atoms.nuclear_repulsion + (P * atoms.h1e).sum() + (P * J).sum() / 2.0)  # train.py:150, molecule.py:727-733
