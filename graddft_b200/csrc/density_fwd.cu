@@ -250,14 +250,16 @@ static int launch_fwd_mt(cudaStream_t stream, const double* DT, FwdParams p) {
   return GDFT_OK;
 }
 
-// 64-row CTAs (three per SM) for the tensor-pipe-bound widths: measured on B200 (tools/rows_probe.py) they match or beat
-// the 128-row shape from n = 264 up at every grid size (62 500 rows, the per-GPU share of the benzene shape on 8 GPUs:
-// 2.74 -> 2.46 ms, because 489 128-row tiles fill 296 slots 1.65 times and cost two full waves; 500 000 rows: 17.65 -> 17.51
-// ms; n = 400, 250 000 rows: 19.88 -> 19.66 ms).  Narrow matrices (n = 100, 40 000 rows: 0.49 -> 0.57 ms) are bound by the
-// per-CTA chain of TMA round trips and epilogue loads, which the smaller tile lengthens: they keep 128 rows.
+// 64-row CTAs (three per SM) for mid-size grids of the tensor-pipe-bound widths.  Measured on B200 (tools/rows_probe.py and
+// the C4 bench line): at 62 500 rows x 264 AOs -- the per-GPU share of the benzene grid on 8 GPUs -- 489 128-row tiles fill the
+// 296 slots 1.65 times and cost two full waves, 2.74 ms; 64-row tiles take 2.46 ms.  At 250 000 ... 500 000 rows the finer
+// tiles are still ahead by 1-3 %; at 2 000 000 x 400 (C4) they lose 2 % (39.6 against 38.8 ms: DRAM traffic drops from 84 to
+// 69 GB, but the halved B-fragment reuse costs more than the shorter tail gains).  Narrow matrices (n = 100, 40 000 rows:
+// 0.49 -> 0.57 ms) are bound by the per-CTA chain of TMA round trips and epilogue loads, which the smaller tile lengthens.
 static bool use_64_rows(int64_t N, int npad) {
   if (const char* e = getenv("GDFT_FWD_ROWS")) { int v = atoi(e); if (v == 64) return true; if (v == 128) return false; }
-  return npad >= 192 && (N + 127) / 128 > 2 * 148;
+  const int64_t t128 = (N + 127) / 128;
+  return npad >= 192 && t128 > 2 * 148 && t128 <= 32 * 148;
 }
 
 template <int NTS>

@@ -7,8 +7,9 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__inst_executed.sum',
         'lts__t_sector_hit_rate.pct', 'dram__cycles_active.avg.pct_of_peak_sustained_elapsed']
 def raw(rep):
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
+    # a .ncu-rep report, or the CSV that `ncu -i report --page raw --csv` printed (reports stay on the GPU box: size)
+    out = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(l for l in out.splitlines() if not l.startswith('==')))
     hdr, units = rows[0], rows[1]
     res = []
     for r in rows[2:]:
