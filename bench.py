@@ -662,7 +662,9 @@ def run_xc(ctx, args, key, extras):
     flop_half = wl["units"] / 2.0 * 2.0 * Nloc * n * n  # half of the build's GEMM units in each of K1 / K2
     ach_bwd, ach_fwd = flop_half / bwd_ms / 1e9, flop_half / fwd_ms / 1e9
     traffic = None
-    tpath = ROOT / "profiles" / "r1_traffic.json"
+    tpath = ROOT / "profiles" / "r2_traffic.json"
+    if not tpath.exists():
+        tpath = ROOT / "profiles" / "r1_traffic.json"
     if world == 1 and tpath.exists():  # dram bytes per launch from the committed ncu --set full capture of this workload
         traffic = json.loads(tpath.read_text()).get(key, {}).get("density_bwd_kernel")
     value = args.steps / (ms_total / 1e3)
