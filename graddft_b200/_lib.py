@@ -69,6 +69,7 @@ SIGNATURES = {
     "gdft_chi_contract": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, _P, _P, c_int64]),
     "gdft_fock_assemble": (c_int, [_P, c_int64, _P, _P, _P, c_double, _P]),
     "gdft_fock_add_sym": (c_int, [_P, c_int64, _P, c_double, _P]),
+    "gdft_aufbau_occupations": (c_int, [_P, c_int64, _P, _P, _P]),
     "gdft_scf_stage_max_n": (c_int, []),
     "gdft_scf_diis_step": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gdft_scf_occupy": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, _P, _P]),

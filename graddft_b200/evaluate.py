@@ -334,7 +334,8 @@ def diff_scf_loop(functional: Functional, cycles: int = 25, **kwargs) -> Callabl
         for cycle in range(cycles):
             fock, diis_data = diis.run((molecule.rdm1, molecule.fock, predicted_e), diis_data, cycle)
             molecule, predicted_e = _scf_body(compute_energy, params, molecule, fock, *args, L_inv=L_inv, warm=warm)
-            norm_gorb = torch.linalg.norm(molecule.get_mo_grads())
+            if cycle == cycles - 1:  # loop state upstream (evaluate.py:1016), but only its last value is ever read
+                norm_gorb = torch.linalg.norm(molecule.get_mo_grads())
         # evaluate.py:1021-1031 runs one more body with fresh DIIS data and then unpacks `final_state`, i.e. discards
         # it; nothing observable depends on that extra iteration, so it is not executed here.
         molecule = molecule.replace(energy=predicted_e)

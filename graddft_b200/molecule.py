@@ -411,6 +411,9 @@ class Molecule:
         return make_rdm1(self.mo_coeff, self.mo_occ)
 
     def get_occ(self) -> Array:
+        if (self.mo_energy.is_cuda and self.mo_energy.dim() == 2 and self.mo_energy.shape[0] == 2 and self.mo_energy.dtype == torch.float64
+                and self.mo_occ.shape == self.mo_energy.shape):
+            return ops.aufbau_occupations(self.mo_energy, self.mo_occ)  # same ranks as the argsort below, one kernel
         nelecs = self.mo_occ.sum(dim=1).round().to(torch.int64)
         return get_occ(self.mo_energy, nelecs, self.mo_occ.shape[1])
 

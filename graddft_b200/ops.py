@@ -1015,6 +1015,16 @@ def scf_stage_supported(t: torch.Tensor, max_diis: int) -> bool:
     return t.is_cuda and t.dtype == F64 and t.shape[-1] <= lib().gdft_scf_stage_max_n() and max_diis <= 16
 
 
+def aufbau_occupations(evals: torch.Tensor, occ_prev: torch.Tensor) -> torch.Tensor:
+    """Aufbau occupations (grad_dft/molecule.py:851-889) by stable rank counting: one small kernel instead of a sort, a
+    scatter and four elementwise launches; no autograd (occupations are piecewise constant)."""
+    evals, occ_prev = _c(evals.detach()), _c(occ_prev.detach())
+    n = int(evals.shape[-1])
+    occ = torch.empty_like(evals)
+    check(lib().gdft_aufbau_occupations(stream_ptr(), n, ptr(evals), ptr(occ_prev), ptr(occ)), "gdft_aufbau_occupations")
+    return occ
+
+
 def scf_diis_step(cycle: int, fock, rdm1, overlap, L_inv, fock_vec, err_vec, gram):
     """One CDIIS step of grad_dft/evaluate.py:1111-1205 on the loop-private ring buffers (updated in place) followed by the
     Cholesky reduction of eigenproblem.py:125-127: returns (C = L^-1 F' L^-T, F', x) -- see gdft_scf_diis_step."""

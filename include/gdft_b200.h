@@ -307,6 +307,10 @@ int gdft_diis_combine(gdft_stream_t stream, int m, int64_t n, const double* x /*
  *   (grad_dft/evaluate.py:1111-1205, grad_dft/utils/eigenproblem.py:125-127).
  * gdft_scf_occupy: mo_coeff = L^-T V, aufbau occupations by stable rank with nelec = round(sum occ_prev), rdm1 = C occ C^T
  *   (eigenproblem.py:129, grad_dft/molecule.py:815-889). */
+/* Aufbau occupations of grad_dft/molecule.py:851-889 for any n (stable rank by counting, no sort): occ[2,n] from evals[2,n]
+ * and nelec_s = round(sum of occ_prev[s,:]). */
+int gdft_aufbau_occupations(gdft_stream_t stream, int64_t n, const double* evals /*[2,n]*/, const double* occ_prev /*[2,n]*/,
+                            double* occ /*[2,n]*/);
 int gdft_scf_stage_max_n(void);
 int gdft_scf_diis_step(gdft_stream_t stream, int64_t n, int m, int cycle, const double* fock /*[2,n,n]*/, const double* rdm1 /*[2,n,n]*/,
                        const double* overlap /*[n,n]*/, const double* L_inv /*[n,n]*/, double* fock_vec /*[m,2,n,n]*/,

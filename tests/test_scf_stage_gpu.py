@@ -107,3 +107,20 @@ def test_fused_loop_in_a_cuda_graph(cuda_device, monkeypatch):
         out = loop(None, m)
     assert loop.last_call_was_graph
     assert abs(float(out.energy) - e_eager) < 1e-10
+
+
+@pytest.mark.parametrize("n", [3, 43, 264, 700])
+def test_aufbau_occupations_match_the_argsort_restatement(cuda_device, n):
+    g = torch.Generator().manual_seed(n)
+    ev = torch.randn(2, n, generator=g, dtype=F64)
+    if n > 4:
+        ev[0, 3] = ev[0, 1]  # exact ties: the stable order decides
+        ev[1, n - 1] = ev[1, 0]
+    occ_prev = torch.zeros(2, n, dtype=F64)
+    occ_prev[0, : max(1, n // 3)] = 1.0
+    occ_prev[1, : max(1, n // 5)] = 1.0
+    want = get_occ(ev, occ_prev.sum(1).round().to(torch.int64), n)
+    got = ops.aufbau_occupations(ev.to(cuda_device), occ_prev.to(cuda_device))
+    assert torch.equal(got.cpu(), want)
+    m = gd.molecule_from_tensors(synthetic_molecule(64, 12, seed=1), cuda_device)
+    assert torch.equal(m.get_occ().cpu(), get_occ(m.mo_energy.cpu(), m.mo_occ.cpu().sum(1).round().to(torch.int64), 12))
