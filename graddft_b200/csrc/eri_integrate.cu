@@ -129,9 +129,17 @@ __global__ void __launch_bounds__(1024) dot_kernel(int64_t n, const double* __re
 __global__ void __launch_bounds__(1024) nonxc_energy_kernel(int64_t n, const double* __restrict__ P, const double* __restrict__ h,
                                                            const double* __restrict__ J, const double* __restrict__ enuc, double* __restrict__ out) {
   __shared__ double red[32];
-  double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += 1024) acc = fma(P[i], fma(0.5, J[i], h[i]), acc);
-  acc = warp_sum(acc);
+  double a4[4] = {0.0, 0.0, 0.0, 0.0};
+  int64_t i = threadIdx.x;
+  for (; i + 3072 < n; i += 4096) {  // four independent loads of each operand in flight
+    double p[4], j[4], hh[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { p[u] = P[i + 1024 * u]; j[u] = J[i + 1024 * u]; hh[u] = h[i + 1024 * u]; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) a4[u] = fma(p[u], fma(0.5, j[u], hh[u]), a4[u]);
+  }
+  for (; i < n; i += 1024) a4[0] = fma(P[i], fma(0.5, J[i], h[i]), a4[0]);
+  double acc = warp_sum((a4[0] + a4[1]) + (a4[2] + a4[3]));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {

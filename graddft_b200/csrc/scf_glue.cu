@@ -14,9 +14,9 @@ namespace gdft {
 // B[0,0] = 0, B[0,1+i] = B[1+i,0] = live_i, B[1+i,1+j] = G_ij, and B[1+i,1+i] = 1 for the slots that are not live yet
 // (live_i = i <= cycle).
 template <bool BORDERED>
-__global__ void __launch_bounds__(256) diis_gram_kernel(int m, int64_t nn, int cycle, const double* __restrict__ e, double* __restrict__ gram) {
-  // one CTA per entry (s, i <= j) of the symmetric Gram matrix: eight warps take an eighth of the n^2 elements each, then a
-  // fixed-order sum.  (One WARP per entry, the first version, left a 10 x 10 x 2 problem on 200 warps: 515 us at n = 264,
+__global__ void __launch_bounds__(1024) diis_gram_kernel(int m, int64_t nn, int cycle, const double* __restrict__ e, double* __restrict__ gram) {
+  // one CTA of 32 warps per entry (s, i <= j) of the symmetric Gram matrix: each warp takes a 32nd of the n^2 elements, then
+  // a fixed-order sum.  (One WARP per entry, the first version, left a 10 x 10 x 2 problem on 200 warps: 515 us at n = 264,
   // 7 % of the benzene-shaped iteration on 8 GPUs, where this n x n work is replicated on every rank.)
   const int npairs = m * (m + 1) / 2;
   const int s = blockIdx.x / npairs;
@@ -24,10 +24,10 @@ __global__ void __launch_bounds__(256) diis_gram_kernel(int m, int64_t nn, int c
   while (rem >= m - i) { rem -= m - i; ++i; }
   const int j = i + rem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ double part[8];
+  __shared__ double part[32];
   const double* a = e + ((size_t)i * 2 + s) * nn;
   const double* b = e + ((size_t)j * 2 + s) * nn;
-  const int64_t chunk = ((nn + 7) / 8 + 31) & ~int64_t(31);
+  const int64_t chunk = ((nn + 31) / 32 + 31) & ~int64_t(31);
   const int64_t k1 = (warp + 1) * chunk < nn ? (warp + 1) * chunk : nn;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   int64_t k = warp * chunk + lane;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) diis_gram_kernel(int m, int64_t nn, int c
   __syncthreads();
   if (threadIdx.x == 0) {
     double v = 0.0;
-    for (int t = 0; t < 8; t++) v += part[t];
+    for (int t = 0; t < 32; t++) v += part[t];
     if (BORDERED) {
       const int mb = m + 1;
       double* B = gram + (size_t)s * mb * mb;
@@ -81,7 +81,7 @@ using namespace gdft;
 extern "C" int gdft_diis_gram(gdft_stream_t stream, int m, int64_t n, const double* err /*[m,2,n,n]*/, double* gram /*[2,m,m]*/) {
   if (m <= 0 || m > 64 || n <= 0 || n > 32768) return GDFT_BAD_SHAPE;
   if (!err || !gram) return GDFT_BAD_ARGUMENT;
-  diis_gram_kernel<false><<<m * (m + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(m, n * n, 0, err, gram);
+  diis_gram_kernel<false><<<m * (m + 1), 1024, 0, static_cast<cudaStream_t>(stream)>>>(m, n * n, 0, err, gram);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
@@ -90,7 +90,7 @@ extern "C" int gdft_diis_matrix(gdft_stream_t stream, int m, int64_t n, int cycl
                                 double* B /*[2,m+1,m+1]*/) {
   if (m <= 0 || m > 64 || n <= 0 || n > 32768) return GDFT_BAD_SHAPE;
   if (!err || !B) return GDFT_BAD_ARGUMENT;
-  diis_gram_kernel<true><<<m * (m + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(m, n * n, cycle, err, B);
+  diis_gram_kernel<true><<<m * (m + 1), 1024, 0, static_cast<cudaStream_t>(stream)>>>(m, n * n, cycle, err, B);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
@@ -437,12 +437,17 @@ __global__ void __launch_bounds__(256) aufbau_occ_kernel(int n, const double* __
     t = warp_sum(t);
     if (threadIdx.x == 0) snel = rint(t);
   }
+  extern __shared__ double sev[];
+  const bool staged = n <= 4096;
+  if (staged)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sev[i] = evals[(size_t)s * n + i];
   __syncthreads();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const double* ev = evals + (size_t)s * n;
+  const double* ev = staged ? sev : evals + (size_t)s * n;
   const double e = ev[j];
   int rank = 0;
+#pragma unroll 4
   for (int i = 0; i < n; i++) {
     const double o = ev[i];
     rank += ((o < e) || (e != e && o == o) || ((o == e || (o != o && e != e)) && i < j)) ? 1 : 0;
@@ -455,7 +460,7 @@ extern "C" int gdft_aufbau_occupations(gdft_stream_t stream, int64_t n, const do
   if (n <= 0 || n > 65536) return GDFT_BAD_SHAPE;
   if (!evals || !occ_prev || !occ) return GDFT_BAD_ARGUMENT;
   dim3 grid((unsigned)((n + 255) / 256), 2);
-  gdft::aufbau_occ_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>((int)n, evals, occ_prev, occ);
+  gdft::aufbau_occ_kernel<<<grid, 256, (n <= 4096 ? (size_t)n * 8 : 0), static_cast<cudaStream_t>(stream)>>>((int)n, evals, occ_prev, occ);
   GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
