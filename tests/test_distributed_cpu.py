@@ -212,3 +212,39 @@ def test_pair_row_sharding_partitions_the_lower_triangle():
     assert part["eri_pair0"] == lo and part["rep_tensor"].shape == (hi - lo, 5, 5)
     rows = gdist.pair_row_indices(5, lo, hi)
     assert torch.equal(part["rep_tensor"], mol["rep_tensor"].reshape(25, 5, 5)[rows])
+
+
+def test_payload_layout_and_exchange_selection_on_cpu():
+    """Host logic of the in-library exchange: 16-byte aligned payload segments, and the fallbacks that keep CPU / gloo runs on
+    the host framework's collective (no library exchange, no graph capture)."""
+    from graddft_b200 import distributed as gdist
+
+    offs, total = gdist.packed_layout([2 * 43 * 43, 1, 43 * 43, 2 * 43 * 43])
+    assert offs == [0, 3698, 3700, 5550] and total == 9248 and all(o % 2 == 0 for o in offs)
+    assert gdist.packed_layout([]) == ([], 0)
+    assert gdist.fock_comm(128, "cpu") is None                      # CPU tensors: torch.distributed
+    assert gdist.exchange_is_capturable("cpu") is False
+    assert gdist.payload_segment(0, [8, 1], "cpu") is None            # no process group: nothing to write into
+    x = [torch.arange(5, dtype=torch.float64), torch.ones(3, dtype=torch.float64)]
+    out = gdist.allreduce_sum_packed(x)                               # world size 1: passed through untouched
+    assert out[0] is x[0] and out[1] is x[1]
+
+
+def test_packed_eri_cache_is_keyed_by_tensor_object_and_version():
+    from graddft_b200 import ops
+
+    cache = []
+    a = torch.zeros(4, 4, 4, 4, dtype=torch.float64)
+    e1 = ops._cache_entry(cache, a, ())
+    assert ops._cache_entry(cache, a, ()) is e1
+    a.add_(1.0)                                                       # in-place edit: a new entry
+    e2 = ops._cache_entry(cache, a, ())
+    assert e2 is not e1
+    b = torch.zeros(4, 4, 4, 4, dtype=torch.float64)
+    assert ops._cache_entry(cache, b, ()) is not e2 and ops._cache_entry(cache, b, (1, None)) is not ops._cache_entry(cache, b, ())
+    del a
+    import gc
+    gc.collect()
+    ops._cache_entry(cache, b, ())
+    assert all(e["ref"]() is not None for e in cache)                 # entries of dead tensors are pruned
+    assert ops.packed_eri_for(b) is None                              # CPU tensor: never packed

@@ -1,10 +1,22 @@
-"""Per-phase clocks of scf_diis_kernel from a -DGDFT_SCF_PROF build (tools/_dev/libgdft_prof.so; development only)."""
-import ctypes, sys
+"""Per-phase clocks of scf_diis_kernel from a -DGDFT_SCF_PROF build of the library (development only; the build is made
+here on first use into tools/_dev/, which is git-ignored)."""
+import ctypes, subprocess, sys
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
 import torch
 from graddft_b200 import _lib
-_lib.LIB_PATH = Path(__file__).resolve().parent / "_dev" / "libgdft_prof.so"
+from graddft_b200.build import build as _build, NVCC_FLAGS, OBJ, CSRC
+DEV = Path(__file__).resolve().parent / "_dev"
+if not (DEV / "libgdft_prof.so").exists():
+    _build()
+    DEV.mkdir(exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    subprocess.run(["nvcc", *flags, "-DGDFT_SCF_PROF", "-c", str(CSRC / "scf_glue.cu"), "-o", str(DEV / "scf_glue_prof.o")], check=True)
+    objs = [str(o) for o in OBJ.glob("*.o") if o.name != "scf_glue.o"]
+    subprocess.run(["nvcc", "-shared", "-o", str(DEV / "libgdft_prof.so"), str(DEV / "scf_glue_prof.o"), *objs,
+                    "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"], check=True)
+_lib.LIB_PATH = DEV / "libgdft_prof.so"
 from graddft_b200 import ops, evaluate
 dev = torch.device("cuda:0"); F64 = torch.float64
 names = ["load", "FD,(FD)S", "err/fock store", "gram", "B build", "LU+solve", "combine+L load", "2 matmuls + store"]
