@@ -37,6 +37,7 @@ SIGNATURES = {
     "gdft_density_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_density_bwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_hf_fock": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t]),
+    "gdft_hf_fock_sum": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_eri_jk": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_eri_j_transpose": (c_int, [_P, c_int64, _P, _P, _P, _P, c_size_t]),
     "gdft_eri_j_rows": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),

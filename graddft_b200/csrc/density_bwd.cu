@@ -49,7 +49,8 @@ struct BwdParams {
 
 // Fragments of one 4-row k-step of one warp: a[i] = A[k][i*8+g], b[j] = sum_q coef_q[k] * plane_q[k][j*8+g]
 // (k = k4*4 + t).  PITCH is the shared-memory row pitch.
-template <int PITCH, int MI, int NJ, int NQ>
+// PS = plane stride in slots between consecutive q: 1 (planes shared by both spins), 2 (per-spin planes, [q][spin] order)
+template <int PITCH, int MI, int NJ, int NQ, int PS = 1>
 __device__ __forceinline__ void bwd_load_frags(double (&a)[MI], double (&b)[NJ], const double* __restrict__ sA,
                                                const double* __restrict__ sP, const double* __restrict__ sC, int k4) {
   constexpr int SLOT_ELEMS = BWD_BKR * PITCH;
@@ -60,7 +61,7 @@ __device__ __forceinline__ void bwd_load_frags(double (&a)[MI], double (&b)[NJ],
   for (int j = 0; j < NJ; j++) {
     double v = c[0] * sP[k4 * 4 * PITCH + j * 8];
 #pragma unroll
-    for (int q = 1; q < NQ; q++) v = fma(c[q], sP[q * SLOT_ELEMS + k4 * 4 * PITCH + j * 8], v);
+    for (int q = 1; q < NQ; q++) v = fma(c[q], sP[q * PS * SLOT_ELEMS + k4 * 4 * PITCH + j * 8], v);
     b[j] = v;
   }
 #pragma unroll
@@ -88,7 +89,7 @@ struct BwdWarpCtx {
 // flattened 4-row k-steps: the fragments of step k+1 (LDS + the in-register combine) are issued before the DMMAs
 // of step k, and at a stage boundary the wait on the next stage's full barrier and its first fragment loads are
 // hoisted above the last DMMA block of the current stage, so the DMMA stream of a warp never drains between stages.
-template <int PITCH, int MI, int NJ, int NQ>
+template <int PITCH, int MI, int NJ, int NQ, int PS = 1>
 __device__ __forceinline__ void bwd_term_loop(double (&acc)[MI][NJ][2], const BwdWarpCtx& w, const BwdTerm& Tm, int& st, uint32_t& ph) {
   constexpr int BKR = BWD_BKR, A_ELEMS = BKR * PITCH, SLOT_ELEMS = BKR * PITCH;
   const int p_off = A_ELEMS + (Tm.per_spin ? w.spin * SLOT_ELEMS : 0) + w.b_off;
@@ -96,24 +97,24 @@ __device__ __forceinline__ void bwd_term_loop(double (&acc)[MI][NJ][2], const Bw
   double a[2][MI], b[2][NJ];
   const double* stage = w.sStage + (size_t)st * w.stage_elems;
   mbar_wait(&w.full[st], ph);
-  bwd_load_frags<PITCH, MI, NJ, NQ>(a[0], b[0], stage + w.a_off, stage + p_off, stage + c_off, 0);
+  bwd_load_frags<PITCH, MI, NJ, NQ, PS>(a[0], b[0], stage + w.a_off, stage + p_off, stage + c_off, 0);
   for (int kt = 0; kt < w.ktiles; kt++) {
     const double* sA = stage + w.a_off;
     const double* sP = stage + p_off;
     const double* sC = stage + c_off;
     const int st_cur = st;
-    bwd_load_frags<PITCH, MI, NJ, NQ>(a[1], b[1], sA, sP, sC, 1);
+    bwd_load_frags<PITCH, MI, NJ, NQ, PS>(a[1], b[1], sA, sP, sC, 1);
     bwd_mma_step<MI, NJ>(acc, a[0], b[0]);
-    bwd_load_frags<PITCH, MI, NJ, NQ>(a[0], b[0], sA, sP, sC, 2);
+    bwd_load_frags<PITCH, MI, NJ, NQ, PS>(a[0], b[0], sA, sP, sC, 2);
     bwd_mma_step<MI, NJ>(acc, a[1], b[1]);
-    bwd_load_frags<PITCH, MI, NJ, NQ>(a[1], b[1], sA, sP, sC, 3);
+    bwd_load_frags<PITCH, MI, NJ, NQ, PS>(a[1], b[1], sA, sP, sC, 3);
     bwd_mma_step<MI, NJ>(acc, a[0], b[0]);
     // advance the ring; prefetch the first fragments of the next stage of this term
     if (++st == w.S) { st = 0; ph ^= 1u; }
     stage = w.sStage + (size_t)st * w.stage_elems;
     if (kt + 1 < w.ktiles) {
       mbar_wait(&w.full[st], ph);
-      bwd_load_frags<PITCH, MI, NJ, NQ>(a[0], b[0], stage + w.a_off, stage + p_off, stage + c_off, 0);
+      bwd_load_frags<PITCH, MI, NJ, NQ, PS>(a[0], b[0], stage + w.a_off, stage + p_off, stage + c_off, 0);
     }
     bwd_mma_step<MI, NJ>(acc, a[1], b[1]);
     __syncwarp();
@@ -136,7 +137,8 @@ __device__ __forceinline__ void bwd_consumer(const BwdParams& p, const BwdWarpCt
   if (w.ktiles > 0) {
     for (int term = 0; term < p.nterms; term++) {
       const BwdTerm Tm = p.terms[term];
-      if (Tm.nq == 1) bwd_term_loop<PITCH, MI, NJ, 1>(acc, w, Tm, st, ph);
+      if (Tm.per_spin && Tm.nq == 2) bwd_term_loop<PITCH, MI, NJ, 2, 2>(acc, w, Tm, st, ph);  // two omegas summed in the GEMM
+      else if (Tm.nq == 1) bwd_term_loop<PITCH, MI, NJ, 1>(acc, w, Tm, st, ph);
       else if (Tm.nq == 4) bwd_term_loop<PITCH, MI, NJ, 4>(acc, w, Tm, st, ph);
       else bwd_term_loop<PITCH, MI, NJ, 5>(acc, w, Tm, st, ph);
     }
@@ -210,7 +212,7 @@ density_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int r = (int)(r_begin + (int64_t)kt * BKR);
         if (it >= S) mbar_wait(&empty[st], ((it / S) - 1) & 1);
         double* sA = sStage + (size_t)st * stage_elems;
-        const int nload = Tm.per_spin ? 2 : Tm.nq;
+        const int nload = Tm.per_spin ? 2 * Tm.nq : Tm.nq;
         mbar_expect_tx(&full[st], (uint32_t)(A_ELEMS + nload * SLOT_ELEMS + COEF_ELEMS) * 8u);
         tma_load_3d(sA, &tmA, &full[st], a0, r, Tm.a_plane);
         for (int q = 0; q < nload; q++) tma_load_3d(sA + A_ELEMS + q * SLOT_ELEMS, &tmP, &full[st], b0, r, Tm.slot_plane0 + q);
@@ -341,12 +343,11 @@ __global__ void bwd_coef_kernel(int64_t N, int64_t Npad, const double* __restric
   for (int i = 0; i < 12; i++) W[(size_t)i * Npad + r] = w[i];
 }
 
-// HF: W[s][r] = g[w][s][r]
-__global__ void hf_coef_kernel(int64_t N, int64_t Npad, const double* __restrict__ g_w, double* __restrict__ W) {
+// HF: W[2 q + s][r] = g[w0 + q][s][r] for q < nw
+__global__ void hf_coef_kernel(int64_t N, int64_t Npad, int nw, const double* __restrict__ g_w, double* __restrict__ W) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= Npad) return;
-  W[r] = r < N ? g_w[r] : 0.0;
-  W[Npad + r] = r < N ? g_w[N + r] : 0.0;
+  for (int q = 0; q < 2 * nw; q++) W[(size_t)q * Npad + r] = r < N ? g_w[(size_t)q * N + r] : 0.0;
 }
 
 struct BwdPlan {
@@ -469,7 +470,10 @@ static int run_bwd(cudaStream_t stream, int64_t N, int n, int nplanes_a, const d
                    int nplanes_b, const double* W, int nterms, const BwdTerm* terms, double scale, double* part, double* out) {
   const int npad = (int)npad_of(n);
   int maxq = 1;
-  for (int i = 0; i < nterms; i++) maxq = terms[i].per_spin ? (maxq > 2 ? maxq : 2) : (terms[i].nq > maxq ? terms[i].nq : maxq);
+  for (int i = 0; i < nterms; i++) {
+    const int need = terms[i].per_spin ? 2 * terms[i].nq : terms[i].nq;
+    maxq = need > maxq ? need : maxq;
+  }
   BwdPlan pl = plan_bwd(N, npad, maxq);
   const int T = 16 * pl.mt;
   const int64_t Npad = round_up(N, BWD_BKR);
@@ -564,11 +568,36 @@ extern "C" int gdft_hf_fock(gdft_stream_t stream_, int64_t N, int64_t n, int Wn,
   if (!W || !part) return GDFT_WORKSPACE_TOO_SMALL;
   const int64_t Npad = round_up(N, BWD_BKR);
   for (int w = 0; w < Wn; w++) {
-    hf_coef_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, stream>>>(N, Npad, g + (size_t)w * 2 * N, W);
+    hf_coef_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, stream>>>(N, Npad, 1, g + (size_t)w * 2 * N, W);
     GDFT_LAUNCH_CHECK();
     BwdTerm term{0, 1, 2 * w, 1, 0};
     int rc = run_bwd(stream, N, (int)n, nplanes, packed, chi_packed, 2 * Wn, W, 1, &term, -0.5, part, fock + (size_t)w * 2 * n * n);
     if (rc) return rc;
   }
   return GDFT_OK;
+}
+
+// sum over omega of the HF Fock terms, F[s] = -1/2 sum_w ao^T diag(g[w,s]) chi[w,s], with the sum taken INSIDE the GEMM for
+// pairs of omegas (M_s = g[w]*chi[w] + g[w+1]*chi[w+1] is formed in registers like the GGA combine): DM21's two omegas cost
+// two GEMM units instead of four.  What dm21_hfgrads_* / b3lyp_hfgrads do with the result of gdft_hf_fock
+// (grad_dft/functional.py:714-717, 755-758: vxc_hf.sum(axis=0)).  An odd omega count leaves a single at the end.
+extern "C" int gdft_hf_fock_sum(gdft_stream_t stream_, int64_t N, int64_t n, int Wn, int nplanes, const double* packed,
+                                const double* chi_packed, const double* g, double* fock_sum, void* ws, size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N <= 0 || n <= 0 || N > (int64_t)2147483000 || n > 32768 || Wn <= 0 || Wn > 2) return GDFT_BAD_SHAPE;
+  if (!packed || !chi_packed || !g || !fock_sum) return GDFT_BAD_ARGUMENT;
+  if (nplanes < 1 || nplanes > 5) return GDFT_BAD_SHAPE;
+  if (!aligned16(packed) || !aligned16(chi_packed) || !aligned16(ws)) return GDFT_BAD_ALIGNMENT;
+  if (ws_bytes < density_bwd_workspace(N, n, 0, 0)) return GDFT_WORKSPACE_TOO_SMALL;
+  const int npad = (int)npad_of(n);
+  BwdPlan pl = plan_bwd(N, npad, BWD_MAX_SLOTS);
+  Workspace wsp(ws, ws_bytes);
+  double* W = wsp.take<double>((size_t)round_up(N, BWD_BKR) * BWD_COEF_W);
+  double* part = wsp.take<double>((size_t)pl.kmax * 2 * npad * npad);
+  if (!W || !part) return GDFT_WORKSPACE_TOO_SMALL;
+  const int64_t Npad = round_up(N, BWD_BKR);
+  hf_coef_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, stream>>>(N, Npad, Wn, g, W);
+  GDFT_LAUNCH_CHECK();
+  BwdTerm term{0, Wn, 0, 1, 0};
+  return run_bwd(stream, N, (int)n, nplanes, packed, chi_packed, 2 * Wn, W, 1, &term, -0.5, part, fock_sum);
 }

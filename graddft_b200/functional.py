@@ -310,6 +310,25 @@ def dm21_hfgrads_cinputs(functional, params, atoms, ehf, cinputs_wout_hf, densit
 _DM21_OMEGAS = (0.0, 0.4)
 
 
+def standard_hf_routes(functional) -> Optional[Sequence[float]]:
+    """The omegas of a functional whose explicit exact-exchange routes are the built-in ones -- V = sum_w hf_fock(dE_xc/d e_HF)[w]
+    through the densities and/or through the coefficient inputs (grad_dft/functional.py:677-758, popular_functionals.py:357-372)
+    -- else None.  For those the predictor may add the two cotangents BEFORE the GEMM (the map g -> V is linear) and take the
+    sum over omega inside it: one two-unit GEMM instead of 2 x len(omegas); the only difference to upstream's term-by-term
+    `fock += V + V^T; abs_clip` is the clip of an intermediate sum at 1e-30."""
+    from . import popular_functionals as pf
+
+    if isinstance(functional, DM21):
+        fields = DM21.__dataclass_fields__
+        same = (functional.densitygrads is fields["densitygrads"].default and functional.coefficient_input_grads is fields["coefficient_input_grads"].default
+                and functional.nograd_densities is fields["nograd_densities"].default
+                and functional.nograd_coefficient_inputs is fields["nograd_coefficient_inputs"].default)
+        return _DM21_OMEGAS if same else None
+    if functional is pf.B3LYP:
+        return (0.0,)
+    return None
+
+
 def _dm21_default_nn(instance, rhoinputs, *_, **__):
     """grad_dft/functional.py:793-822: log|x|+eps -> dense -> tanh -> 6 x (dense + res -> LayerNorm -> act) -> head."""
     x = canonicalize_inputs(rhoinputs)

@@ -368,6 +368,11 @@ class Molecule:
             m[key] = ops.density_forward(basis, self.rdm1, GDFT_HF)[4]
         return m[key]
 
+    def hf_fock_summed(self, omegas, g: Array) -> Array:
+        """sum over omega of -1/2 ao^T diag(g[w,s]) chi[w,s] ([2,n,n]) for a cotangent g[len(omegas), 2, N] that is already at hand
+        (the predictor's merged exact-exchange routes): one GEMM of two units for up to two omegas."""
+        return ops.hf_fock_sum(self.packed_basis.select_chi(self._omega_indices(omegas)), g)
+
     def HF_density_grad_2_Fock(self, functional, params, omegas, ehf, coefficient_inputs, densities_wout_hf, **kwargs) -> Array:
         basis = self.packed_basis.select_chi(self._omega_indices(omegas))
         b = self._memo().get("xc_build")

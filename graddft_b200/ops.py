@@ -257,6 +257,24 @@ def hf_fock(basis: PackedBasis, g: torch.Tensor) -> torch.Tensor:
     return _HFFock.apply(g, basis)
 
 
+def hf_fock_sum(basis: PackedBasis, g: torch.Tensor) -> torch.Tensor:
+    """sum_w F[w] of `hf_fock` -- what the hybrid wiring does with it (grad_dft/functional.py:714-717, 755-758) -- with the sum
+    over omega taken inside the GEMM for up to two omegas (gdft_hf_fock_sum); no autograd (first-order predictor path)."""
+    if basis.chi_packed is None:
+        raise ValueError("Precomputed chi tensor has not been loaded.")
+    g = _c(g.detach())
+    if tuple(g.shape) != (basis.W, 2, basis.N):
+        raise TypeError(f"g must be [{basis.W}, 2, {basis.N}], got {tuple(g.shape)}")
+    if basis.W > 2:
+        return _hf_fock_raw(basis, g).sum(dim=0)
+    out = torch.empty((2, basis.n, basis.n), dtype=F64, device=basis.device)
+    ws = workspace(lib().gdft_workspace_bytes(_lib.OP_HF_FOCK, basis.N, basis.n, 0, basis.W), basis.device)
+    with _timed("gdft_hf_fock"):
+        check(lib().gdft_hf_fock_sum(stream_ptr(), basis.N, basis.n, basis.W, basis.nplanes, ptr(basis.planes), ptr(basis.chi_packed), ptr(g),
+                                     ptr(out), wptr(ws), ws.numel()), "gdft_hf_fock_sum")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 # ERI sweep
 # ---------------------------------------------------------------------------------------------------------

@@ -107,6 +107,16 @@ def energy_predictor(functional: Functional, nlc_functional=None, clip_cte: floa
         build = at._memo().get("xc_build") if not differentiable else None
         if build is not None and build.matches(functional, params):
             # same rdm1, same params: the features are the ones the XC build just evaluated (pure functions of them)
+            from .functional import standard_hf_routes
+            omegas = standard_hf_routes(functional)
+            gs = [g for g, route in ((build.g_densities, functional.densitygrads), (build.g_cinputs, functional.coefficient_input_grads))
+                  if route and g is not None]
+            n_routes = int(bool(functional.densitygrads)) + int(bool(functional.coefficient_input_grads))
+            if omegas is not None and gs and len(gs) == n_routes and at.rdm1.is_cuda and all(tuple(g.shape) == tuple(gs[0].shape) for g in gs):
+                # built-in routes: both cotangents dE_xc/d e_HF are by-products of the build's backward pass and V is linear in
+                # them -- one GEMM for all routes and omegas (functional.standard_hf_routes)
+                with torch.no_grad():
+                    return [at.hf_fock_summed(omegas, gs[0] if len(gs) == 1 else gs[0] + gs[1])]
             terms = []
             with torch.no_grad():
                 if functional.densitygrads:

@@ -132,6 +132,10 @@ int gdft_density_bwd(gdft_stream_t stream, int64_t N, int64_t n, int flags, int 
 int gdft_hf_fock(gdft_stream_t stream, int64_t N, int64_t n, int W, int nplanes, const double* packed,
                  const double* chi_packed, const double* g /*[W,2,N]*/, double* fock /*[W,2,n,n]*/,
                  void* ws, size_t ws_bytes);
+/* sum over omega of the above, F[s] = sum_w F[w,s] (what grad_dft/functional.py:714-717, 755-758 do with it: vxc_hf.sum(axis=0)),
+ * with the sum taken inside the GEMM: W <= 2 omegas cost two GEMM units, not 2 W. */
+int gdft_hf_fock_sum(gdft_stream_t stream, int64_t N, int64_t n, int W, int nplanes, const double* packed,
+                     const double* chi_packed, const double* g /*[W,2,N]*/, double* fock_sum /*[2,n,n]*/, void* ws, size_t ws_bytes);
 
 /* ---- K3: ERI sweep ---------------------------------------------------------------------------
  * J[p,q] = sum_rt eri[p,q,r,t] P[r,t]  (coulomb_potential, grad_dft/molecule.py:811);

@@ -131,3 +131,16 @@ def test_density_forward_row_tile_shapes_agree_bitwise(cuda_device, N, n, seed, 
         assert torch.equal(a, b)
     assert relerr(got[0], oracle.density(mol["rdm1"], mol["ao"])) < RTOL
     assert relerr(got[2], oracle.kinetic_density(mol["rdm1"], mol["grad_ao"])) < RTOL
+
+
+@pytest.mark.parametrize("N,n,W", [(1000, 12, 2), (777, 43, 1), (1500, 264, 2), (900, 80, 3)])
+def test_hf_fock_summed_over_omega_inside_the_gemm(cuda_device, N, n, W):
+    """gdft_hf_fock_sum: sum_w -1/2 ao^T diag(g[w,s]) chi[w,s] with the omega sum formed in registers (two omegas per GEMM) against
+    the per-omega kernel summed afterwards and against the oracle (grad_dft/molecule.py:606-613 + functional.py:714-717)."""
+    mol = synthetic_molecule(N, n, n_omega=W, seed=1984 + W, with_eri=False)
+    basis = ops.PackedBasis(mol["ao"].to(cuda_device), mol["grad_ao"].to(cuda_device), None, mol["chi"].to(cuda_device))
+    g = torch.randn(W, 2, N, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    got = ops.hf_fock_sum(basis, g.to(cuda_device))
+    ref = oracle.HF_fock(mol["chi"], g, mol["ao"]).sum(dim=0)
+    assert relerr(got, ref) < RTOL
+    assert relerr(got, ops.hf_fock(basis, g.to(cuda_device)).sum(dim=0).cpu()) < RTOL
