@@ -125,6 +125,24 @@ def test_c3_eri_sweep_full_size(cuda_device):
     # grad_dft/molecule.py:811 on the sampled rows: J[p,q] = sum_rt (pq|rt) P[r,t]
     ref = oracle.coulomb_potential(P2.cpu(), eri.reshape(n * n, n, n)[rows].cpu().reshape(len(rows), 1, n, n)).reshape(-1)
     assert rel(J2.reshape(-1)[rows].cpu(), ref) < 1e-12
+    # the packed sweep at full size (9.79 GB of pair rows for the 38.9 GB tensor): symmetry check on the device, the same J from
+    # a quarter of the bytes, both triangles from one packed entry, and the policy (packed from the second use on)
+    asym, big = ops.eri_symmetry_defect(eri, n)
+    assert asym <= 1e-13 * big
+    pe = ops.PackedERI.from_rows(eri, n)
+    assert pe.complete and pe.packed.numel() * 8 == 9788803200
+    with torch.no_grad():
+        Jp, EJp = pe.coulomb(P1, want_energy=True)
+        Jp2 = pe.coulomb(P2)
+    assert rel(Jp, J1) < 1e-13 and rel(Jp2, J2) < 1e-13 and torch.equal(Jp2, Jp2.T)
+    assert abs(float(EJp) - float(EJ)) < 1e-12 * abs(float(EJ))
+    del pe
+    ops.release_packed_eri()
+    with torch.no_grad():
+        ops.coulomb_j_and_energy(P1, eri)                   # first use of this tensor object: the plain sweep
+        Jq, _ = ops.coulomb_j_and_energy(P1, eri)           # second use: checked, packed, swept packed
+    assert ops.packed_eri_for(eri, count_use=False) is not None and rel(Jq, J1) < 1e-13
+    ops.release_packed_eri()
     del eri
     torch.cuda.empty_cache()
 
