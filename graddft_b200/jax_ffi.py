@@ -11,7 +11,10 @@ Two layers:
 2. **JAX wrappers** (need `import jax`; JAX is not installed in this repository's build/test environment, SURVEY.md
    section 0.4): `register()` once per process, then the functions below.  Each linear kernel is wrapped with its transpose
    as custom VJP (and vice versa, so `grad(grad(.))` closes over the same two kernels); the per-point maps are bound to
-   second order (`pointwise` -> `gdft_pointwise_bwd` -> `gdft_pointwise_bwd2`).  Nothing here contains arithmetic.
+   second order (`pointwise` -> `gdft_pointwise_bwd` -> `gdft_pointwise_bwd2`).  Nothing here contains arithmetic.  The
+   wrappers themselves are executed by tests/test_jax_wrappers_gpu.py on a minimal stand-in for `custom_vjp` / `ffi_call`
+   (tests/jax_min_shim.py) that routes every call through the real adapters: values, forward/backward rules and their
+   nesting are compared with the torch bindings.  What remains unexercised is JAX's own tracing (jit / grad composition).
 
     from graddft_b200 import jax_ffi
     jax_ffi.register()
