@@ -305,8 +305,12 @@ __global__ void __launch_bounds__(SCF_THREADS) scf_diis_kernel(const DiisArgs a)
   }
   __syncthreads();
   STAMP();
-  {  // LU with partial pivoting on [B | e_0] (LAPACK's pivot rule: the first largest |entry|; rows scaled by the reciprocal
-     // pivot as dgetf2 does), then back substitution; one thread per element of the trailing block
+  // LU with partial pivoting on [B | e_0] (LAPACK's pivot rule: the first largest |entry|; rows scaled by the reciprocal pivot
+  // as dgetf2 does), then back substitution; one thread per element of the trailing block.  Only the first LU_THREADS threads
+  // take part and they meet at a named barrier: the ~60 barriers of the elimination cost a third of a CTA-wide one each
+  constexpr int LU_THREADS = 320;  // >= (SCF_MAX_M) * (SCF_MAX_M + 2) trailing elements
+#define LU_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(LU_THREADS) : "memory")
+  if (tid < LU_THREADS) {
     const int w = mb + 1;
     for (int k = 0; k < mb; k++) {
       if (warp == 0) {
@@ -322,28 +326,30 @@ __global__ void __launch_bounds__(SCF_THREADS) scf_diis_kernel(const DiisArgs a)
         }
         if (lane == 0) { sPiv = arg; sRpiv = 1.0 / sBmat[arg * w + k]; }
       }
-      __syncthreads();
+      LU_SYNC();
       const int arg = sPiv;
       if (arg != k) {  // uniform branch
         if (tid < w) { const double t = sBmat[k * w + tid]; sBmat[k * w + tid] = sBmat[arg * w + tid]; sBmat[arg * w + tid] = t; }
-        __syncthreads();
+        LU_SYNC();
       }
       const int wk = w - k - 1;                    // trailing columns k+1 .. w-1 (the right-hand side included)
       const int r = k + 1 + tid / wk, c = k + 1 + tid % wk;
       double v = 0.0;
       if (r < mb) v = fma(-(sBmat[r * w + k] * sRpiv), sBmat[k * w + c], sBmat[r * w + c]);
-      __syncthreads();
+      LU_SYNC();
       if (r < mb) sBmat[r * w + c] = v;
       if (tid == 0) sRdiag[k] = sRpiv;
-      __syncthreads();
+      LU_SYNC();
     }
     for (int r = mb - 1; r >= 0; r--) {
       if (tid == 0) sx[r] = sBmat[r * w + mb] * sRdiag[r];
-      __syncthreads();
+      LU_SYNC();
       if (tid < r) sBmat[tid * w + mb] = fma(-sBmat[tid * w + r], sx[r], sBmat[tid * w + mb]);
-      __syncthreads();
+      LU_SYNC();
     }
   }
+#undef LU_SYNC
+  __syncthreads();
   STAMP();
   if (tid < m) a.x_out[s * m + tid] = sx[1 + tid];
   // F' = sum_i x_i F_i in logical order (evaluate.py:1198)
