@@ -74,6 +74,8 @@ SIGNATURES = {
     "gdft_scf_stage_max_n": (c_int, []),
     "gdft_scf_diis_step": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gdft_scf_occupy": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "gdft_xc_point_workspace": (c_size_t, [c_int64]),
+    "gdft_xc_point_fused": (c_int, [_P, c_int64, c_int, c_double, ctypes.POINTER(c_double), c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_nonxc_energy": (c_int, [_P, c_int64, _P, _P, _P, _P, _P]),
     "gdft_eri_npair": (c_int64, [c_int64]),
     "gdft_eri_packed_bytes": (c_size_t, [c_int64, c_int64]),

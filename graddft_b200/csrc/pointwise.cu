@@ -149,6 +149,111 @@ __global__ void __launch_bounds__(128) pointwise_bwd_kernel(const PwArgs a) {
   if (a.tau_bar) reinterpret_cast<double2*>(a.tau_bar)[r] = (needs & 4) ? make_double2(d[4], d[5]) : make_double2(0.0, 0.0);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// First-order XC build of a closed-form functional in ONE pass per grid point (value + VJP): features on dual numbers (their
+// values ARE the forward pass), the optional exact-exchange column h = sum_{w,s} e_HF[w,s,r] (popular_functionals.py:330-338),
+// abs_clip of the densities (functional.py:160-185), e = sum_f c_f d_f with a constant coefficient row, abs_clip of e and of the
+// quadrature weight, E = sum_r w_r e_r (functional.py:219-253, 316-342) -- and, because the seed of the reverse pass is known
+// per point (dE/dd_f = w_r [|e_r| > clip] c_f [|d_f| > clip]), the cotangents of rho / grad_rho / tau / lapl and of e_HF in the
+// same thread.  Replaces pointwise_fwd + cat + abs_clip + integrate_fwd + integrate_bwd + abs_clip' + slice copies + pointwise_bwd
+// (ten launches, two evaluations of the formulas) inside the predictor's first-order path; same per-point arithmetic as those
+// kernels (same templates, same fma order over the columns).
+// ---------------------------------------------------------------------------------------------------------------------
+struct XcPointArgs {
+  int64_t N;
+  double clip;
+  int W;  // number of omegas of the exact-exchange column (0: none)
+  double coef[8];
+  const double *rho, *grho, *tau, *lapl, *ehf, *w;
+  double *partial, *rho_bar, *grho_bar, *tau_bar, *lapl_bar, *ehf_bar;
+};
+
+template <int ID>
+__global__ void __launch_bounds__(128) xc_point_kernel(const XcPointArgs a) {
+  constexpr int F = PwCols<ID>::F, FE = PwCols<ID>::FE;
+  const int needs = pointwise_needs(ID);
+  typedef Dual<6> D6;
+  __shared__ double red[4];
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double contrib = 0.0;
+  if (r < a.N) {
+    const double2 rho = reinterpret_cast<const double2*>(a.rho)[r];
+    double g[6] = {0, 0, 0, 0, 0, 0};
+    double x[6] = {rho.x, rho.y, 0, 0, 0, 0};
+    if (needs & 1) {
+#pragma unroll
+      for (int q = 0; q < 6; q++) g[q] = a.grho[r * 6 + q];
+      x[2] = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+      x[3] = g[3] * g[3] + g[4] * g[4] + g[5] * g[5];
+    }
+    if (needs & 2) { const double2 l = reinterpret_cast<const double2*>(a.lapl)[r]; x[4] = l.x; x[5] = l.y; }
+    if (needs & 4) { const double2 l = reinterpret_cast<const double2*>(a.tau)[r]; x[4] = l.x; x[5] = l.y; }
+    D6 v[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) v[q] = pw::Make<D6>::variable(x[q], q);
+    D6 feats[FE];
+    eval_features<ID, D6>(v, a.clip, feats);
+    double e = 0.0, seed[FE];
+#pragma unroll
+    for (int f = 0; f < FE; f++) {
+      const double raw = feats[f].v;
+      const bool m = fabs(raw) > a.clip;
+      e = fma(a.coef[f], m ? raw : 0.0, e);
+      seed[f] = m ? a.coef[f] : 0.0;
+    }
+    double h = 0.0;
+    bool mh = false;
+    if (a.W > 0) {
+      for (int q = 0; q < 2 * a.W; q++) h += a.ehf[(size_t)q * a.N + r];
+      mh = fabs(h) > a.clip;
+      e = fma(a.coef[F], mh ? h : 0.0, e);
+    }
+    const double wr = a.w[r];
+    const double wc = fabs(wr) > a.clip ? wr : 0.0;
+    const bool live = fabs(e) > a.clip;
+    contrib = live ? wc * e : 0.0;
+    const double eb = live ? wc : 0.0;
+    double d[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int f = 0; f < FE; f++) {
+      const double ob = eb * seed[f];
+#pragma unroll
+      for (int q = 0; q < 6; q++) d[q] = fma(ob, feats[f].d[q], d[q]);
+    }
+    if (a.rho_bar) reinterpret_cast<double2*>(a.rho_bar)[r] = make_double2(d[0], d[1]);
+    if (a.grho_bar) {
+      double* o = a.grho_bar + r * 6;
+#pragma unroll
+      for (int j = 0; j < 3; j++) { o[j] = 2.0 * d[2] * g[j]; o[3 + j] = 2.0 * d[3] * g[3 + j]; }
+    }
+    if (a.lapl_bar) reinterpret_cast<double2*>(a.lapl_bar)[r] = (needs & 2) ? make_double2(d[4], d[5]) : make_double2(0.0, 0.0);
+    if (a.tau_bar) reinterpret_cast<double2*>(a.tau_bar)[r] = (needs & 4) ? make_double2(d[4], d[5]) : make_double2(0.0, 0.0);
+    if (a.W > 0 && a.ehf_bar) {
+      const double hb = mh ? eb * a.coef[F] : 0.0;
+      for (int q = 0; q < 2 * a.W; q++) a.ehf_bar[(size_t)q * a.N + r] = hb;
+    }
+  }
+  contrib = warp_sum(contrib);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) a.partial[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// E = sum of the per-CTA partial sums: one CTA, fixed order
+__global__ void __launch_bounds__(1024) xc_point_sum_kernel(int64_t count, const double* __restrict__ partial, double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < count; i += 1024) acc += partial[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v2 = red[threadIdx.x];
+    v2 = warp_sum(v2);
+    if (threadIdx.x == 0) out[0] = v2;
+  }
+}
+
 // VJP of pointwise_bwd_kernel.  With X = (rho, grad_rho, x) the inputs, ob the output cotangent and
 // Xbar(X, ob) = J(X)^T ob the first-order result, this kernel receives the cotangent U of Xbar and returns
 //   ob_bar[f] = (J U)_f                      (a directional derivative: the inner dual part of the value)
@@ -415,4 +520,44 @@ extern "C" int gdft_pointwise_bwd2(gdft_stream_t stream, int64_t N, int id, doub
   a.u_rho = u_rho; a.u_grho = u_grad_rho; a.u_tau = u_tau; a.u_lapl = u_lapl;
   a.out_bar_bar = out_bar_bar; a.rho_t = rho_t; a.grho_t = grad_rho_t; a.tau_t = tau_t; a.lapl_t = lapl_t;
   return dispatch_pw2(static_cast<cudaStream_t>(stream), id, a);
+}
+
+// First-order XC build of a closed-form functional in one pass (see xc_point_kernel): E_xc and the cotangents of the grid
+// quantities (and of e_HF when an exact-exchange column with W omegas is present).  coef: F feature coefficients followed,
+// when W > 0, by the coefficient of the exact-exchange column.  Workspace: ceil(N / 128) doubles.
+extern "C" size_t gdft_xc_point_workspace(int64_t N) { return N > 0 ? (size_t)((N + 127) / 128) * 8 + 256 : 0; }
+
+extern "C" int gdft_xc_point_fused(gdft_stream_t stream_, int64_t N, int id, double clip, const double* coef, int ncoef, const double* rho,
+                                   const double* grad_rho, const double* tau, const double* lapl, const double* ehf, int W, const double* w,
+                                   double* E, double* rho_bar, double* grad_rho_bar, double* tau_bar, double* lapl_bar, double* ehf_bar,
+                                   void* ws, size_t ws_bytes) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  int rc = check_pw_inputs(N, id, rho, grad_rho, tau, lapl);
+  if (rc) return rc;
+  const int F = pointwise_ncols(id);
+  if (id == GDFT_PW_DM21_INPUTS || F <= 0 || F > 7 || W < 0 || W > 8 || ncoef != F + (W > 0 ? 1 : 0)) return GDFT_BAD_SHAPE;
+  if (!coef || !w || !E || !rho_bar || (W > 0 && (!ehf || !ehf_bar))) return GDFT_BAD_ARGUMENT;
+  if (!aligned16(rho_bar) || !aligned16(tau_bar) || !aligned16(lapl_bar)) return GDFT_BAD_ALIGNMENT;
+  if (ws_bytes < gdft_xc_point_workspace(N)) return GDFT_WORKSPACE_TOO_SMALL;
+  XcPointArgs a{};
+  a.N = N; a.clip = clip; a.W = W;
+  for (int i = 0; i < ncoef; i++) a.coef[i] = coef[i];
+  a.rho = rho; a.grho = grad_rho; a.tau = tau; a.lapl = lapl; a.ehf = ehf; a.w = w;
+  a.partial = static_cast<double*>(ws);
+  a.rho_bar = rho_bar; a.grho_bar = grad_rho_bar; a.tau_bar = tau_bar; a.lapl_bar = lapl_bar; a.ehf_bar = ehf_bar;
+  const unsigned grid = (unsigned)((N + 127) / 128);
+  switch (id) {
+    case GDFT_PW_LSDA_X: xc_point_kernel<GDFT_PW_LSDA_X><<<grid, 128, 0, st>>>(a); break;
+    case GDFT_PW_B88_X: xc_point_kernel<GDFT_PW_B88_X><<<grid, 128, 0, st>>>(a); break;
+    case GDFT_PW_VWN_C: xc_point_kernel<GDFT_PW_VWN_C><<<grid, 128, 0, st>>>(a); break;
+    case GDFT_PW_LYP_C: xc_point_kernel<GDFT_PW_LYP_C><<<grid, 128, 0, st>>>(a); break;
+    case GDFT_PW_PW92_C: xc_point_kernel<GDFT_PW_PW92_C><<<grid, 128, 0, st>>>(a); break;
+    case GDFT_PW_B3LYP_SET: xc_point_kernel<GDFT_PW_B3LYP_SET><<<grid, 128, 0, st>>>(a); break;
+    case GDFT_PW_B88_SET: xc_point_kernel<GDFT_PW_B88_SET><<<grid, 128, 0, st>>>(a); break;
+    default: return GDFT_BAD_ARGUMENT;
+  }
+  GDFT_LAUNCH_CHECK();
+  xc_point_sum_kernel<<<1, 1024, 0, st>>>((int64_t)grid, a.partial, E);
+  GDFT_LAUNCH_CHECK();
+  return GDFT_OK;
 }

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import contextlib
 
-from typing import Optional, Tuple
+from typing import Sequence, Optional, Tuple
 
 import torch
 from torch.autograd import Function
@@ -396,6 +396,35 @@ def coulomb_j_and_energy(P: torch.Tensor, eri: torch.Tensor) -> Tuple[torch.Tens
         return pe.coulomb(P.detach(), want_energy=True)
     J, EJ = _eri_j_raw(P.detach(), eri.detach(), want_energy=True)
     return J, EJ[0]
+
+
+def xc_point_fused(name: str, clip: float, coef: Sequence[float], rho, grad_rho, tau, lapl, ehf, weights):
+    """(E_xc, rho_bar, grad_rho_bar, tau_bar, lapl_bar, ehf_bar) of a closed-form functional with the constant coefficient row
+    `coef` in one pass per grid point (gdft_xc_point_fused); no autograd -- the predictor's first-order path."""
+    import ctypes
+
+    L = lib()
+    pid = _lib.PW_IDS[name]
+    rho = _c(rho.detach())
+    N = int(rho.shape[0])
+    grad_rho = _c(grad_rho.detach()) if grad_rho is not None else None
+    tau = _c(tau.detach()) if tau is not None else None
+    lapl = _c(lapl.detach()) if lapl is not None else None
+    ehf = _c(ehf.detach()) if ehf is not None else None
+    W = int(ehf.shape[0]) if ehf is not None else 0
+    weights = _c(weights.detach())
+    dev = rho.device
+    E = torch.empty((1,), dtype=F64, device=dev)
+    rb = torch.empty_like(rho)
+    gb = torch.empty_like(grad_rho) if grad_rho is not None else None
+    tb = torch.empty_like(tau) if tau is not None else None
+    lb = torch.empty_like(lapl) if lapl is not None else None
+    eb = torch.empty_like(ehf) if ehf is not None else None
+    ws = workspace(L.gdft_xc_point_workspace(N), dev)
+    carr = (ctypes.c_double * len(coef))(*[float(c) for c in coef])
+    check(L.gdft_xc_point_fused(stream_ptr(), N, pid, float(clip), carr, len(coef), ptr(rho), ptr(grad_rho), ptr(tau), ptr(lapl), ptr(ehf), W,
+                                ptr(weights), ptr(E), ptr(rb), ptr(gb), ptr(tb), ptr(lb), ptr(eb), wptr(ws), ws.numel()), "gdft_xc_point_fused")
+    return E[0], rb, gb, tb, lb, eb
 
 
 def nonxc_energy(P: torch.Tensor, h1e: torch.Tensor, J: torch.Tensor, nuclear_repulsion) -> torch.Tensor:

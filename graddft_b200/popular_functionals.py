@@ -126,3 +126,17 @@ B3LYP = Functional(
     needs_omegas=(0.0,),
 )
 PW92 = Functional(coefficients=_one, energy_densities=pw92_densities, needs=("rho",))
+
+
+def fused_xc_spec(functional):
+    """(pointwise set, constant coefficient row, omegas of the exact-exchange column or None) for the closed-form functionals of
+    this module, whose first-order XC build the predictor runs as ONE per-point kernel (ops.xc_point_fused) instead of the
+    generic features -> combine -> clip -> quadrature -> autograd chain; None for anything else (user-defined functionals,
+    neural functionals).  The rows are the very numbers `coefficients` returns."""
+    a0, ax, ac = 0.2, 0.72, 0.81
+    table = ((LSDA, "LSDA_X", (1.0,), None), (B88, "B88_SET", (1.0, 1.0), None), (VWN, "VWN_C", (1.0,), None), (LYP, "LYP_C", (1.0,), None),
+             (PW92, "PW92_C", (1.0,), None), (B3LYP, "B3LYP_SET", (1 - a0, ax, 1 - ac, ac, a0), (0.0,)))
+    for fun, name, row, omegas in table:
+        if functional is fun:
+            return name, row, omegas
+    return None

@@ -8,6 +8,7 @@ merges them -- SURVEY.md Appendix B).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -35,6 +36,11 @@ def xc_energy_and_grads(functional: Functional, params, rdm1: Array, atoms: Mole
     (densities -> features -> E_xc) + VJP (-> V_xc [2,n,n], un-symmetrised).  Also returns the molecule
     carrying the differentiated rdm1 (its cached grid quantities are reused by the hybrid terms)."""
     keep_exc_graph = torch.is_grad_enabled() and (_requires_grad(params) or rdm1.requires_grad)
+    if not keep_exc_graph and not create_graph and not args and not functional_kwargs and rdm1.is_cuda and os.environ.get("GDFT_FUSED_XC", "1") != "0":
+        from .popular_functionals import fused_xc_spec
+        spec = fused_xc_spec(functional)
+        if spec is not None:
+            return _fused_xc_build(functional, spec, params, rdm1, atoms)
     if create_graph is None:
         # V_xc itself differentiable (w.r.t. params and rdm1) only when the density matrix already carries a graph,
         # i.e. inside a differentiable SCF loop (evaluate.py:917-1038); energy-only losses need first order only
@@ -73,6 +79,28 @@ def xc_energy_and_grads(functional: Functional, params, rdm1: Array, atoms: Mole
             (fock_xc,) = torch.autograd.grad(exc, leaf, create_graph=create_graph, retain_graph=keep_exc_graph or create_graph)
     if not (keep_exc_graph or create_graph):
         exc = exc.detach()  # otherwise E_xc stays differentiable w.r.t. params (first order: energy losses, train.py:312-359)
+    return exc, fock_xc, at
+
+
+def _fused_xc_build(functional, spec, params, rdm1: Array, atoms: Molecule):
+    """The first-order XC build of a closed-form functional as K1 -> ONE per-point kernel -> K2 (popular_functionals.fused_xc_spec,
+    ops.xc_point_fused): the same arithmetic as the generic chain of xc_energy_and_grads, evaluated once per point.  Leaves the
+    cotangent at the exact-exchange stop_gradient boundary on the molecule for the explicit Fock term, like the generic path."""
+    from ._lib import GDFT_GRAD, GDFT_HF, GDFT_LAPL, GDFT_RHO
+
+    name, row, omegas = spec
+    at = atoms.replace(rdm1=rdm1.detach())
+    want_grad = name in ("B88_X", "LYP_C", "B3LYP_SET", "B88_SET")
+    want_lapl = name in ("LYP_C", "B3LYP_SET")
+    flags = GDFT_RHO | (GDFT_GRAD if want_grad else 0) | (GDFT_LAPL if want_lapl else 0) | (GDFT_HF if omegas else 0)
+    basis = at.packed_basis.select_chi(at._omega_indices(omegas)) if omegas else at.packed_basis
+    with torch.no_grad():
+        rho, grho, _, lapl, ehf = ops._density_fwd_raw(basis, at.rdm1, flags)
+        exc, rb, gb, _, lb, eb = ops.xc_point_fused(name, 1e-30, row, rho, grho, None, lapl, ehf, at.grid.weights)
+        fock_xc = ops.density_transpose(basis, rb, gb, None, lb)
+    at._memo()["xc_build"] = XCBuild(
+        functional=functional, params_key=_params_key(params), clip=1e-30, coefficients=None, grad_densities=None, nograd_densities=None,
+        densities_raw=None, grad_cinputs=None, nograd_cinputs=None, cinputs=None, g_densities=eb, g_cinputs=None)
     return exc, fock_xc, at
 
 

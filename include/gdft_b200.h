@@ -213,6 +213,18 @@ int gdft_pointwise_bwd2(gdft_stream_t stream, int64_t N, int id, double clip, co
                         const double* u_rho, const double* u_grad_rho, const double* u_tau, const double* u_lapl,
                         double* out_bar_bar, double* rho_t, double* grad_rho_t, double* tau_t, double* lapl_t);
 
+/* First-order XC build of a closed-form functional with a constant coefficient row in ONE pass per grid point: the features
+ * of `id` (evaluated once, on dual numbers), the optional exact-exchange column h = sum_{w,s} ehf[w,s,r]
+ * (popular_functionals.py:330-338), abs_clip of the densities (functional.py:160-185), e = sum_f coef_f d_f, abs_clip of e and of
+ * the weights, E = sum_r w_r e_r (functional.py:219-253, 316-342), and the cotangents of the grid quantities and of ehf seeded by
+ * dE/dd_f = w_r [|e_r| > clip] coef_f [|d_f| > clip].  coef holds the F feature coefficients and, when W > 0, the coefficient of
+ * the exact-exchange column.  Same per-point arithmetic as gdft_pointwise_fwd/_bwd + gdft_xc_integrate_fwd/_bwd. */
+size_t gdft_xc_point_workspace(int64_t N);
+int gdft_xc_point_fused(gdft_stream_t stream, int64_t N, int id, double clip, const double* coef_host, int ncoef, const double* rho,
+                        const double* grad_rho, const double* tau, const double* lapl, const double* ehf /*[W,2,N] or NULL*/, int W,
+                        const double* weights, double* E /*[1]*/, double* rho_bar, double* grad_rho_bar, double* tau_bar,
+                        double* lapl_bar, double* ehf_bar /*[W,2,N] or NULL*/, void* ws, size_t ws_bytes);
+
 /* ---- coefficient-network residual block ----------------------------
  * out = elu(LayerNorm(y + res) * scale + bias) over the last axis of [N, W] (W even, <= 512), the loop body of DM21's
  * default_nn after its Dense layer (grad_dft/functional.py:809-819; flax LayerNorm: biased variance, eps inside the

@@ -36,6 +36,35 @@ def test_shard_tensors_and_pack_roundtrip():
     assert float(e2) == float(e) and torch.equal(v2, v)
 
 
+def _run_world(target, world, *extra, attempts=3):
+    """Spawn `world` gloo ranks of `target(rank, world, port, q, *extra)` and collect one result per rank (sorted by rank).  The
+    free-port probe can lose a race with another process and the first `import torch` of a spawned child can take a minute on
+    a cold container, so a failed rendezvous is retried on a fresh port instead of failing the suite."""
+    last = None
+    for _ in range(attempts):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=target, args=(r, world, port, q, *extra)) for r in range(world)]
+        [p.start() for p in procs]
+        try:
+            res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+            [p.join(timeout=120) for p in procs]
+            if all(p.exitcode == 0 for p in procs):
+                return res
+            last = RuntimeError(f"rank exit codes {[p.exitcode for p in procs]}")
+        except Exception as exc:  # queue.Empty: a rank never reported
+            last = exc
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+            p.join(timeout=30)
+    raise AssertionError(f"world-size-{world} run of {target.__name__} failed {attempts} times: {last!r}")
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -50,17 +79,7 @@ def _worker(rank, world, port, q):
 
 
 def test_allreduce_xc_world2_gloo():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    [p.start() for p in procs]
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    [p.join(timeout=60) for p in procs]
-    assert all(p.exitcode == 0 for p in procs)
+    res = _run_world(_worker, 2)
     e_tot = res[0][1] + res[1][1]
     v_tot = res[0][2] + res[1][2]
     for r in res:
@@ -90,17 +109,7 @@ def _grad_worker(rank, world, port, q):
 
 
 def test_allreduce_gradients_world2_gloo():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
-    [p.start() for p in procs]
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    [p.join(timeout=60) for p in procs]
-    assert all(p.exitcode == 0 for p in procs)
+    res = _run_world(_grad_worker, 2)
     for k in range(2):
         tot = res[0][1][k] + res[1][1][k]
         assert torch.allclose(res[0][3][k], tot, rtol=0, atol=1e-15) and torch.allclose(res[1][3][k], tot, rtol=0, atol=1e-15)
@@ -131,17 +140,7 @@ def _packed_worker(rank, world, port, q):
 
 
 def test_allreduce_sum_packed_world2_gloo():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_packed_worker, args=(r, 2, port, q)) for r in range(2)]
-    [p.start() for p in procs]
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    [p.join(timeout=60) for p in procs]
-    assert all(p.exitcode == 0 for p in procs)
+    res = _run_world(_packed_worker, 2)
     for k in (0, 1, 3):
         tot = res[0][1][k] + res[1][1][k]
         for r in res:
@@ -173,17 +172,7 @@ def _spin_split_worker(rank, world, port, q):
 def test_spin_split_fock_solver_gloo(world):
     """The sharded SCF iteration's eigensolve: rank 0 solves spin 0, rank 1 spin 1, one all-reduce with a single non-zero
     contributor per entry -- every rank ends with the bits the unsplit solver produces (host logic; gloo on CPU)."""
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_spin_split_worker, args=(r, world, port, q)) for r in range(world)]
-    [p.start() for p in procs]
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    [p.join(timeout=60) for p in procs]
-    assert all(p.exitcode == 0 for p in procs)
+    res = _run_world(_spin_split_worker, world)
     for rank, w, C, w0, C0 in res:
         assert torch.equal(w, res[0][1]) and torch.equal(C, res[0][2])      # replicated bit for bit
         assert torch.allclose(w, w0, rtol=0, atol=1e-13)

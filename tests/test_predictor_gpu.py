@@ -275,3 +275,36 @@ def test_harris_energy_parameter_gradient_matches_finite_differences(cuda_device
         exc = fun.energy_xc_only(params, m)
         slope_exc = sum(float((g * direction[k]).sum()) for g, k in zip(torch.autograd.grad(exc, list(params.values())), params))
         assert abs(slope - slope_exc) > 1e-6 * max(1.0, abs(fd))
+
+
+@pytest.mark.parametrize("name", ["LSDA", "B88", "VWN", "LYP", "PW92", "B3LYP"])
+def test_fused_xc_build_matches_the_generic_chain(cuda_device, name, monkeypatch):
+    """The one-pass first-order XC build of the closed-form functionals (gdft_xc_point_fused behind train.xc_energy_and_grads)
+    against the generic features -> combine -> clip -> quadrature -> autograd chain it replaces: E_xc, V_xc, the cotangent at the
+    exact-exchange boundary and the whole predictor; masked (exactly zero density) rows included."""
+    from graddft_b200.train import xc_energy_and_grads
+
+    fun = dict(FUNCS, B3LYP=gd.B3LYP)[name]
+    mol = synthetic_molecule(3001, 23, n_omega=1, seed=1993, mask_frac=0.01)
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GDFT_FUSED_XC", mode)
+        with torch.no_grad():
+            exc, vxc, at = xc_energy_and_grads(fun, None, m.rdm1, m)
+            e, f = gd.energy_predictor(fun)(None, m)
+        res[mode] = (exc, vxc, at._memo()["xc_build"].g_densities if name == "B3LYP" else None, e, f)
+    a, b = res["1"], res["0"]
+    assert abs(float(a[0]) - float(b[0])) <= 1e-12 * abs(float(b[0]))
+    assert relerr(a[1], b[1].cpu()) < 1e-12
+    if name == "B3LYP":
+        assert relerr(a[2], b[2].cpu()) < 1e-13
+    assert abs(float(a[3]) - float(b[3])) < 1e-10 and relerr(a[4], b[4].cpu()) < 1e-11
+    # against the oracle on a grid without exactly-zero densities (there the reference's own derivative is NaN: DESIGN.md section 4)
+    monkeypatch.setenv("GDFT_FUSED_XC", "1")
+    mol = synthetic_molecule(3001, 23, n_omega=1, seed=1994, mask_frac=0.0)
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    with torch.no_grad():
+        e, f = gd.energy_predictor(fun)(None, m)
+    e_ref, f_ref = oracle.predict_b3lyp(mol) if name == "B3LYP" else oracle.predict_semilocal(mol, name)
+    assert abs(float(e) - float(e_ref)) < E_TOL and relerr(f, f_ref) < F_RTOL
