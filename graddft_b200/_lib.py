@@ -39,6 +39,7 @@ SIGNATURES = {
     "gdft_hf_fock": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_hf_fock_sum": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t]),
     "gdft_eri_jk": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t]),
+    "gdft_eri_k_transpose": (c_int, [_P, c_int64, _P, _P, _P, _P, c_size_t]),
     "gdft_eri_j_transpose": (c_int, [_P, c_int64, _P, _P, _P, _P, c_size_t]),
     "gdft_eri_j_rows": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "gdft_eri_j_transpose_rows": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, c_size_t]),
@@ -105,7 +106,7 @@ SIGNATURES = {
 # XLA custom-call adapters: void(stream, void** buffers, const char* opaque, size_t opaque_len)
 for _name in ("pack_basis", "pack_chi", "density_fwd", "density_bwd", "hf_fock", "eri_j", "eri_j_transpose", "xc_integrate_fwd", "xc_integrate_bwd",
               "pointwise_fwd", "pointwise_bwd", "pointwise_bwd2", "eri_j_rows", "eri_j_transpose_rows", "ln_elu_fwd", "ln_elu_bwd",
-            "dense_ln_elu_fwd", "dense_ln_elu_bwd", "sym_eigh", "chi_contract", "diis_gram", "diis_combine"):
+            "dense_ln_elu_fwd", "dense_ln_elu_bwd", "sym_eigh", "chi_contract", "diis_gram", "diis_combine", "eri_jk", "eri_k_transpose"):
     SIGNATURES[f"gdft_{_name}_xla"] = (None, [_P, ctypes.POINTER(_P), c_char_p, c_size_t])
 
 _lib = None

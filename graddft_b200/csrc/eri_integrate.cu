@@ -149,22 +149,177 @@ __global__ void __launch_bounds__(1024) nonxc_energy_kernel(int64_t n, const dou
   }
 }
 
-// K[p][r] += sum_t eri[p][q][r][t] P[q][t]  for all q: one CTA per (p, r-block); not in the reference
-//  -- same ERI stream with the other index pairing.
-__global__ void __launch_bounds__(256) eri_k_kernel(int n, const double* __restrict__ eri, const double* __restrict__ P,
-                                                   double* __restrict__ K) {
-  // warp w of the CTA handles r = blockIdx.y*8 + w; loops over q; lanes stride t
-  const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.y * 8 + warp;
-  if (r >= n) return;
-  double acc = 0.0;
-  for (int q = 0; q < n; q++) {
-    const double* e = eri + (((size_t)p * n + q) * n + r) * n;
-    const double* pq = P + (size_t)q * n;
-    for (int t = lane; t < n; t += 32) acc = fma(__ldcs(e + t), __ldg(pq + t), acc);
+// ---------------------------------------------------------------------------------------------------
+// J AND K from ONE pass over the tensor (BASELINE.json north_star "J/K"; K is not in the reference):
+//   J[p][q] = sum_{r,t} eri[p][q][r][t] P[r][t]      K[p][r] = sum_{q,t} eri[p][q][r][t] P[q][t]
+// The (p,q) block [r][t] is n x n contiguous doubles.  CTA = (p, chunk of q), two q per step.  A warp takes four rows r of
+// both blocks at a time (eight 128-bit streaming loads per lane and t-slice in flight); P[r][:] is read once for the two
+// blocks (L2), P[q][:] and P[q+1][:] sit in shared memory.  J: lane-local over the whole block, one warp + CTA reduction per
+// block.  K: one lane-partial per row, the four rows reduced together by a butterfly (6 shuffles per 4 rows instead of 20),
+// accumulated over q in shared memory by the warp that owns the row; the q-chunks' partial K are summed in fixed order by
+// sum_splits_kernel.  8 n^4 bytes for both results.
+// ---------------------------------------------------------------------------------------------------
+constexpr int JK_THREADS = 256;
+constexpr int JK_ROWS = 4;
+constexpr int JK_MAX_SPLIT = 16;
+
+template <bool VEC>
+__global__ void __launch_bounds__(JK_THREADS, 2) eri_jk_kernel(int n, int qsplit, int qper, const double* __restrict__ eri,
+                                                              const double* __restrict__ P, double* __restrict__ J,
+                                                              double* __restrict__ Kpart) {
+  extern __shared__ __align__(16) double jk_smem[];
+  const int npad = (n + 1) & ~1;
+  double* sPq0 = jk_smem;
+  double* sPq1 = jk_smem + npad;
+  double* sK = jk_smem + 2 * npad;
+  __shared__ double sJ[JK_THREADS / 32][2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p = blockIdx.x / qsplit, s = blockIdx.x % qsplit;
+  const int q0 = s * qper, q1 = min(n, q0 + qper);
+  const int ngroups = (n + JK_ROWS - 1) / JK_ROWS;
+  const size_t nn = (size_t)n * n;
+  for (int r = tid; r < n; r += JK_THREADS) sK[r] = 0.0;
+  for (int q = q0; q < q1; q += 2) {
+    const bool has1 = q + 1 < q1;
+    __syncthreads();
+    for (int i = tid; i < npad; i += JK_THREADS) {
+      sPq0[i] = i < n ? P[(size_t)q * n + i] : 0.0;
+      sPq1[i] = (has1 && i < n) ? P[(size_t)(q + 1) * n + i] : 0.0;
+    }
+    __syncthreads();
+    const double* b0 = eri + ((size_t)p * n + q) * nn;
+    const double* b1 = has1 ? b0 + nn : b0;  // odd tail: the second block repeats the first with zero weights
+    double j0 = 0.0, j1 = 0.0;
+    for (int g = warp; g < ngroups; g += JK_THREADS / 32) {
+      const int r0 = g * JK_ROWS;
+      double k[JK_ROWS];
+#pragma unroll
+      for (int u = 0; u < JK_ROWS; u++) k[u] = 0.0;
+      if (VEC) {
+        const int n2 = n >> 1;
+        for (int i = lane; i < n2; i += 32) {
+          const double2 w0 = reinterpret_cast<const double2*>(sPq0)[i], w1 = reinterpret_cast<const double2*>(sPq1)[i];
+          double2 e0[JK_ROWS], e1[JK_ROWS], pr[JK_ROWS];
+#pragma unroll
+          for (int u = 0; u < JK_ROWS; u++) {
+            if (r0 + u < n) {  // warp-uniform
+              const size_t off = (size_t)(r0 + u) * n;
+              e0[u] = __ldcs(reinterpret_cast<const double2*>(b0 + off) + i);
+              e1[u] = __ldcs(reinterpret_cast<const double2*>(b1 + off) + i);
+              pr[u] = __ldg(reinterpret_cast<const double2*>(P + off) + i);
+            } else {
+              e0[u] = e1[u] = pr[u] = make_double2(0.0, 0.0);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < JK_ROWS; u++) {
+            j0 = fma(e0[u].x, pr[u].x, fma(e0[u].y, pr[u].y, j0));
+            j1 = fma(e1[u].x, pr[u].x, fma(e1[u].y, pr[u].y, j1));
+            k[u] = fma(e0[u].x, w0.x, fma(e0[u].y, w0.y, fma(e1[u].x, w1.x, fma(e1[u].y, w1.y, k[u]))));
+          }
+        }
+      } else {
+        for (int i = lane; i < n; i += 32) {
+          const double w0 = sPq0[i], w1 = sPq1[i];
+          double e0[JK_ROWS], e1[JK_ROWS], pr[JK_ROWS];
+#pragma unroll
+          for (int u = 0; u < JK_ROWS; u++) {
+            if (r0 + u < n) {
+              const size_t off = (size_t)(r0 + u) * n + i;
+              e0[u] = __ldcs(b0 + off);
+              e1[u] = __ldcs(b1 + off);
+              pr[u] = __ldg(P + off);
+            } else {
+              e0[u] = e1[u] = pr[u] = 0.0;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < JK_ROWS; u++) {
+            j0 = fma(e0[u], pr[u], j0);
+            j1 = fma(e1[u], pr[u], j1);
+            k[u] = fma(e0[u], w0, fma(e1[u], w1, k[u]));
+          }
+        }
+      }
+      // four lane-partials per lane -> one row total per group of eight lanes: halve the value count at xor 16 and xor 8
+      // (each lane passes on the half it does not keep), then plain butterflies
+      {
+        const bool hi = lane & 16;
+        const double a0 = (hi ? k[2] : k[0]) + __shfl_xor_sync(0xffffffffu, hi ? k[0] : k[2], 16);
+        const double a1 = (hi ? k[3] : k[1]) + __shfl_xor_sync(0xffffffffu, hi ? k[1] : k[3], 16);
+        const bool hi2 = lane & 8;
+        double v = (hi2 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi2 ? a0 : a1, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        const int r = r0 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+        if ((lane & 7) == 0 && r < n) sK[r] += v;  // row r belongs to this warp for every q: no race
+      }
+    }
+    j0 = warp_sum(j0);
+    j1 = warp_sum(j1);
+    if (lane == 0) { sJ[warp][0] = j0; sJ[warp][1] = j1; }
+    __syncthreads();
+    if (tid < 2 && (tid == 0 || has1)) {
+      double acc = 0.0;
+#pragma unroll
+      for (int w = 0; w < JK_THREADS / 32; w++) acc += sJ[w][tid];
+      J[(size_t)p * n + q + tid] = acc;
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) K[(size_t)p * n + r] = acc;
+  __syncthreads();
+  for (int r = tid; r < n; r += JK_THREADS) Kpart[((size_t)s * n + p) * n + r] = sK[r];
+}
+
+// Cotangent of K wrt P for ANY tensor: Pbar[q][t] = sum_{p,r} eri[p][q][r][t] Kbar[p][r].  CTA = (q, chunk of p); a thread owns
+// one t-slice (the CTA spans whole rows, so the stream is contiguous), eight rows in flight; p-chunks summed in fixed order.
+template <bool VEC>
+__global__ void __launch_bounds__(256) eri_kt_kernel(int n, int psplit, int pper, const double* __restrict__ eri,
+                                                    const double* __restrict__ Kbar, double* __restrict__ part) {
+  const int q = blockIdx.x / psplit, s = blockIdx.x % psplit;
+  const int p0 = s * pper, p1 = min(n, p0 + pper);
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  const size_t nn = (size_t)n * n;
+  if (VEC) {
+    if (i >= (n >> 1)) return;
+    double2 acc = make_double2(0.0, 0.0);
+    for (int p = p0; p < p1; p++) {
+      const double2* base = reinterpret_cast<const double2*>(eri + ((size_t)p * n + q) * nn) + i;
+      const double* kb = Kbar + (size_t)p * n;
+      const int n2 = n >> 1;
+      int r = 0;
+      for (; r + 8 <= n; r += 8) {
+        double2 e[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) e[u] = __ldcs(base + (size_t)(r + u) * n2);
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const double w = __ldg(kb + r + u); acc.x = fma(w, e[u].x, acc.x); acc.y = fma(w, e[u].y, acc.y); }
+      }
+      for (; r < n; r++) {
+        const double2 e = __ldcs(base + (size_t)r * n2);
+        const double w = __ldg(kb + r);
+        acc.x = fma(w, e.x, acc.x); acc.y = fma(w, e.y, acc.y);
+      }
+    }
+    reinterpret_cast<double2*>(part + ((size_t)s * n + q) * n)[i] = acc;
+  } else {
+    if (i >= n) return;
+    double acc = 0.0;
+    for (int p = p0; p < p1; p++) {
+      const double* base = eri + ((size_t)p * n + q) * nn + i;
+      const double* kb = Kbar + (size_t)p * n;
+      int r = 0;
+      for (; r + 8 <= n; r += 8) {
+        double e[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) e[u] = __ldcs(base + (size_t)(r + u) * n);
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc = fma(__ldg(kb + r + u), e[u], acc);
+      }
+      for (; r < n; r++) acc = fma(__ldg(kb + r), __ldcs(base + (size_t)r * n), acc);
+    }
+    part[((size_t)s * n + q) * n + i] = acc;
+  }
 }
 
 size_t eri_workspace(int64_t n) {
@@ -481,23 +636,64 @@ extern "C" int gdft_eri_j_packed(gdft_stream_t stream_, int64_t n, int64_t pair0
   return GDFT_OK;
 }
 
+// chunks of the second index for the J+K sweep / the K transpose: enough CTAs for a few waves, at most JK_MAX_SPLIT partials
+static void jk_split(int64_t n, int unit, int* split, int* per) {
+  int want = (int)imin64(JK_MAX_SPLIT, imax64(1, (8 * 148 + n - 1) / n));
+  int per_ = (int)((n + want - 1) / want);
+  per_ = ((per_ + unit - 1) / unit) * unit;
+  *per = per_;
+  *split = (int)((n + per_ - 1) / per_);
+}
+
 extern "C" int gdft_eri_jk(gdft_stream_t stream_, int64_t n, const double* eri, const double* P, double* J, double* K,
                            double* EJ, void* ws, size_t ws_bytes) {
-  (void)ws; (void)ws_bytes;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n <= 0 || n > 2048) return GDFT_BAD_SHAPE;
   if (!eri || !P || !J) return GDFT_BAD_ARGUMENT;
   const int64_t R = n * n;
-  if (int rc = eri_j_rows_launch(stream, n, R, eri, P, J)) return rc;
   if (K) {
-    dim3 g((unsigned)n, (unsigned)((n + 7) / 8));
-    eri_k_kernel<<<g, 256, 0, stream>>>((int)n, eri, P, K);
+    // both contractions from one pass over the tensor
+    if (!ws || ws_bytes < eri_workspace(n)) return GDFT_WORKSPACE_TOO_SMALL;
+    int qsplit, qper;
+    jk_split(n, 2, &qsplit, &qper);
+    double* Kpart = static_cast<double*>(ws);
+    const size_t smem = (size_t)3 * ((n + 1) & ~(int64_t)1) * sizeof(double);
+    const bool vec = (n % 2 == 0) && aligned16(eri) && aligned16(P);
+    const unsigned grid = (unsigned)(n * qsplit);
+    if (vec) eri_jk_kernel<true><<<grid, JK_THREADS, smem, stream>>>((int)n, qsplit, qper, eri, P, J, Kpart);
+    else eri_jk_kernel<false><<<grid, JK_THREADS, smem, stream>>>((int)n, qsplit, qper, eri, P, J, Kpart);
     GDFT_LAUNCH_CHECK();
+    sum_splits_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, qsplit, Kpart, K);
+    GDFT_LAUNCH_CHECK();
+  } else {
+    if (int rc = eri_j_rows_launch(stream, n, R, eri, P, J)) return rc;
   }
   if (EJ) {
     dot_kernel<<<1, 1024, 0, stream>>>(R, P, J, 0.5, EJ);
     GDFT_LAUNCH_CHECK();
   }
+  return GDFT_OK;
+}
+
+extern "C" int gdft_eri_k_transpose(gdft_stream_t stream_, int64_t n, const double* eri, const double* Kbar, double* Pbar, void* ws,
+                                    size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || n > 2048) return GDFT_BAD_SHAPE;
+  if (!eri || !Kbar || !Pbar) return GDFT_BAD_ARGUMENT;
+  if (!ws || ws_bytes < eri_workspace(n)) return GDFT_WORKSPACE_TOO_SMALL;
+  int psplit, pper;
+  jk_split(n, 1, &psplit, &pper);
+  double* part = static_cast<double*>(ws);
+  const bool vec = (n % 2 == 0) && aligned16(eri);
+  const int slices = vec ? (int)(n / 2) : (int)n;
+  const int threads = (int)imin64(256, ((slices + 31) / 32) * 32);
+  dim3 grid((unsigned)(n * psplit), (unsigned)((slices + threads - 1) / threads));
+  if (vec) eri_kt_kernel<true><<<grid, threads, 0, stream>>>((int)n, psplit, pper, eri, Kbar, part);
+  else eri_kt_kernel<false><<<grid, threads, 0, stream>>>((int)n, psplit, pper, eri, Kbar, part);
+  GDFT_LAUNCH_CHECK();
+  const int64_t C = n * n;
+  sum_splits_kernel<<<(unsigned)((C + 255) / 256), 256, 0, stream>>>(C, psplit, part, Pbar);
+  GDFT_LAUNCH_CHECK();
   return GDFT_OK;
 }
 

@@ -87,6 +87,20 @@ extern "C" void gdft_eri_j_xla(gdft_stream_t s, void** b, const char* opaque, si
   int rc = gdft_eri_jk(s, d.n, (const double*)b[0], (const double*)b[1], (double*)b[2], nullptr, (double*)b[3], nullptr, 0);
   finish(rc, (cudaStream_t)s, b[2]);
 }
+// operands: eri, P | results: J, K, ws   (both contractions from one pass over the tensor)
+extern "C" void gdft_eri_jk_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_eri_jk(s, d.n, (const double*)b[0], (const double*)b[1], (double*)b[2], (double*)b[3], nullptr, b[4], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[2]);
+}
+// operands: eri, Kbar | results: Pbar, ws
+extern "C" void gdft_eri_k_transpose_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
+  XlaDims d;
+  if (!dims_ok(opaque, len, &d)) return;
+  int rc = gdft_eri_k_transpose(s, d.n, (const double*)b[0], (const double*)b[1], (double*)b[2], b[3], d.ws_bytes);
+  finish(rc, (cudaStream_t)s, b[2]);
+}
 // operands: eri, Jbar | results: Pbar, ws
 extern "C" void gdft_eri_j_transpose_xla(gdft_stream_t s, void** b, const char* opaque, size_t len) {
   XlaDims d;

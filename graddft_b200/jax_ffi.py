@@ -43,7 +43,7 @@ except ImportError:  # the only supported state here
 
 _TARGETS = ("pack_basis", "pack_chi", "density_fwd", "density_bwd", "hf_fock", "eri_j", "eri_j_transpose", "xc_integrate_fwd",
             "xc_integrate_bwd", "pointwise_fwd", "pointwise_bwd", "pointwise_bwd2", "eri_j_rows", "eri_j_transpose_rows", "ln_elu_fwd",
-            "ln_elu_bwd", "dense_ln_elu_fwd", "dense_ln_elu_bwd", "sym_eigh", "chi_contract", "diis_gram", "diis_combine")
+            "ln_elu_bwd", "dense_ln_elu_fwd", "dense_ln_elu_bwd", "sym_eigh", "chi_contract", "diis_gram", "diis_combine", "eri_jk", "eri_k_transpose")
 # struct XlaDims { int64 N, n, F, c_rows; int32 flags, nplanes, W, id; double clip; uint64 ws_bytes; }  (jax_ffi.cu)
 _DIMS = struct.Struct("<qqqqiiiidQ")
 F64, U8 = "float64", "uint8"
@@ -118,6 +118,18 @@ def plan_eri_j_transpose(n) -> Plan:
     """operands: eri, J_bar | results: P_bar, ws."""
     ws = _ws(_lib.OP_ERI_J, 0, n, 0, 0)
     return Plan("eri_j_transpose", 2, (((n, n), F64), ((ws,), U8)), pack_dims(n=n, ws_bytes=ws))
+
+
+def plan_eri_jk(n) -> Plan:
+    """operands: eri[n, n, n, n], P[n, n] | results: J[n, n], K[n, n], ws (one pass over the tensor for both)."""
+    ws = _ws(_lib.OP_ERI_J, 0, n, 0, 0)
+    return Plan("eri_jk", 2, (((n, n), F64), ((n, n), F64), ((ws,), U8)), pack_dims(n=n, ws_bytes=ws))
+
+
+def plan_eri_k_transpose(n) -> Plan:
+    """operands: eri, K_bar | results: P_bar, ws."""
+    ws = _ws(_lib.OP_ERI_J, 0, n, 0, 0)
+    return Plan("eri_k_transpose", 2, (((n, n), F64), ((ws,), U8)), pack_dims(n=n, ws_bytes=ws))
 
 
 def plan_eri_j_rows(n, rows) -> Plan:
@@ -355,6 +367,29 @@ def coulomb_j(rep_tensor, P):  # pragma: no cover
     j.defvjp(lambda Pm: (j(Pm), None), lambda _, Jb: (jt(Jb),))
     jt.defvjp(lambda Jb: (jt(Jb), None), lambda _, pb: (j(pb),))
     return j(P)
+
+
+def coulomb_jk(rep_tensor, P):  # pragma: no cover
+    """(J, K): J_pq = sum_rt (pq|rt) P_rt and K_pr = sum_qt (pq|rt) P_qt from one pass over rep_tensor (BASELINE.json's "J/K"; the
+    reference never forms K from rep_tensor).  Both are linear in P: the VJP is the sum of the two transposed sweeps."""
+    n = P.shape[-1]
+
+    @jax.custom_vjp
+    def jt(Jb):
+        return _run(plan_eri_j_transpose(n), rep_tensor, Jb)[0]
+
+    @jax.custom_vjp
+    def kt(Kb):
+        return _run(plan_eri_k_transpose(n), rep_tensor, Kb)[0]
+
+    @jax.custom_vjp
+    def jk(Pm):
+        return tuple(_run(plan_eri_jk(n), rep_tensor, Pm)[:2])
+
+    jk.defvjp(lambda Pm: (jk(Pm), None), lambda _, bars: (jt(bars[0]) + kt(bars[1]),))
+    jt.defvjp(lambda Jb: (jt(Jb), None), lambda _, pb: (jk(pb)[0],))
+    kt.defvjp(lambda Kb: (kt(Kb), None), lambda _, pb: (jk(pb)[1],))
+    return jk(P)
 
 
 def coulomb_j_rows(rep_rows, P):  # pragma: no cover

@@ -378,15 +378,80 @@ def coulomb_j_rows(P: torch.Tensor, eri_rows: torch.Tensor) -> torch.Tensor:
     return _CoulombJRows.apply(P, eri_rows)
 
 
-def coulomb_k(P: torch.Tensor, eri: torch.Tensor) -> torch.Tensor:
-    """K[p,r] = sum_qt (pq|rt) P[q,t]: same sweep, other index pairing (not in the reference; no VJP bound)."""
-    L = lib()
-    P, eri = _c(P.detach()), _c(eri.detach())
+def _eri_shapes(P, eri):
     n = int(P.shape[0])
+    if tuple(eri.shape) != (n, n, n, n) or tuple(P.shape) != (n, n):
+        raise TypeError(f"rep_tensor must be [n,n,n,n] and the matrix [n,n]; got {tuple(eri.shape)}, {tuple(P.shape)}")
+    return n
+
+
+def _eri_jk_raw(P, eri):
+    """(J, K) from ONE pass over the tensor (gdft_eri_jk with K requested)."""
+    L = lib()
+    P, eri = _c(P), _c(eri)
+    n = _eri_shapes(P, eri)
     J = torch.empty((n, n), dtype=F64, device=P.device)
     K = torch.empty((n, n), dtype=F64, device=P.device)
-    check(L.gdft_eri_jk(stream_ptr(), n, ptr(eri), ptr(P), ptr(J), ptr(K), None, None, 0), "gdft_eri_jk")
-    return K
+    ws = workspace(L.gdft_workspace_bytes(_lib.OP_ERI_J, 0, n, 0, 0), P.device)
+    with _timed("gdft_eri_jk"):
+        check(L.gdft_eri_jk(stream_ptr(), n, ptr(eri), ptr(P), ptr(J), ptr(K), None, wptr(ws), ws.numel()), "gdft_eri_jk")
+    return J, K
+
+
+def _eri_kt_raw(Kbar, eri):
+    L = lib()
+    Kbar, eri = _c(Kbar), _c(eri)
+    n = _eri_shapes(Kbar, eri)
+    out = torch.empty((n, n), dtype=F64, device=Kbar.device)
+    ws = workspace(L.gdft_workspace_bytes(_lib.OP_ERI_J, 0, n, 0, 0), Kbar.device)
+    check(L.gdft_eri_k_transpose(stream_ptr(), n, ptr(eri), ptr(Kbar), ptr(out), wptr(ws), ws.numel()), "gdft_eri_k_transpose")
+    return out
+
+
+class _CoulombJK(Function):
+    """(J, K) of one sweep; each output's cotangent goes back through its own transposed sweep (both linear in P, so
+    autograd of any order closes over the same four kernels)."""
+
+    @staticmethod
+    def forward(ctx, P, eri):
+        ctx.save_for_backward(eri)
+        ctx.set_materialize_grads(False)
+        return _eri_jk_raw(P, eri)
+
+    @staticmethod
+    def backward(ctx, Jbar, Kbar):
+        (eri,) = ctx.saved_tensors
+        out = None
+        if Jbar is not None:
+            out = _CoulombJT.apply(Jbar, eri)
+        if Kbar is not None:
+            kt = _CoulombKT.apply(Kbar, eri)
+            out = kt if out is None else out + kt
+        return out, None
+
+
+class _CoulombKT(Function):
+    @staticmethod
+    def forward(ctx, Kbar, eri):
+        ctx.save_for_backward(eri)
+        return _eri_kt_raw(Kbar, eri)
+
+    @staticmethod
+    def backward(ctx, g):
+        (eri,) = ctx.saved_tensors
+        return _CoulombJK.apply(g, eri)[1], None
+
+
+def coulomb_jk(P: torch.Tensor, eri: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """J[p,q] = sum_rt (pq|rt) P[r,t] and K[p,r] = sum_qt (pq|rt) P[q,t] from one pass over rep_tensor (8 n^4 bytes for both);
+    differentiable to any order w.r.t. P.  K is the exchange pairing named by BASELINE.json's north_star; the reference itself
+    never contracts rep_tensor this way."""
+    return _CoulombJK.apply(P, eri)
+
+
+def coulomb_k(P: torch.Tensor, eri: torch.Tensor) -> torch.Tensor:
+    """K[p,r] = sum_qt (pq|rt) P[q,t] (see coulomb_jk)."""
+    return _CoulombJK.apply(P, eri)[1]
 
 
 def coulomb_j_and_energy(P: torch.Tensor, eri: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -138,14 +138,20 @@ int gdft_hf_fock_sum(gdft_stream_t stream, int64_t N, int64_t n, int W, int npla
                      const double* chi_packed, const double* g /*[W,2,N]*/, double* fock_sum /*[2,n,n]*/, void* ws, size_t ws_bytes);
 
 /* ---- K3: ERI sweep ---------------------------------------------------------------------------
- * J[p,q] = sum_rt eri[p,q,r,t] P[r,t]  (coulomb_potential, grad_dft/molecule.py:811);
- * optionally K[p,r] = sum_qt eri[p,q,r,t] P[q,t] from the same pass (not in the reference; see
- * SURVEY.md section 0.3) and E_J = 1/2 <P,J> (grad_dft/molecule.py:781-783).  K and EJ may be NULL. */
+ * J[p,q] = sum_rt eri[p,q,r,t] P[r,t]  (coulomb_potential, grad_dft/molecule.py:811) and E_J = 1/2 <P,J>
+ * (grad_dft/molecule.py:781-783).  With K != NULL the same ONE pass over the tensor also returns
+ * K[p,r] = sum_qt eri[p,q,r,t] P[q,t] (the exchange pairing of BASELINE.json's "J/K"; not in the reference, SURVEY.md
+ * section 0.3): 8 n^4 bytes for both.  K needs the gdft_workspace_bytes(GDFT_OP_ERI_J, ...) workspace (partial K per chunk
+ * of q, summed in fixed order); J-only calls need none.  J of a J+K call and of a J-only call differ in summation order
+ * (rounding level), each is run-to-run reproducible.  K and EJ may be NULL. */
 int gdft_eri_jk(gdft_stream_t stream, int64_t n, const double* eri /*[n,n,n,n]*/, const double* P /*[n,n]*/,
                 double* J /*[n,n]*/, double* K /*[n,n] or NULL*/, double* EJ /*[1] or NULL*/,
                 void* ws, size_t ws_bytes);
 /* cotangent of the sweep wrt P: Pbar[r,t] = sum_pq Jbar[p,q] eri[p,q,r,t] (exact for any eri) */
 int gdft_eri_j_transpose(gdft_stream_t stream, int64_t n, const double* eri, const double* Jbar,
+                         double* Pbar, void* ws, size_t ws_bytes);
+/* cotangent of K wrt P: Pbar[q,t] = sum_pr Kbar[p,r] eri[p,q,r,t] (exact for any eri; same workspace) */
+int gdft_eri_k_transpose(gdft_stream_t stream, int64_t n, const double* eri, const double* Kbar,
                          double* Pbar, void* ws, size_t ws_bytes);
 
 /* Row-sharded sweep (at n = 400 the tensor is 205 GB and must be split over GPUs):
@@ -405,6 +411,8 @@ void gdft_density_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaq
 void gdft_hf_fock_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_eri_j_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_eri_j_transpose_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_eri_jk_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+void gdft_eri_k_transpose_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_xc_integrate_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_xc_integrate_bwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
 void gdft_pointwise_fwd_xla(gdft_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);

@@ -27,7 +27,7 @@ def jx(cuda_device, monkeypatch):
     monkeypatch.setattr(jax_ffi, "HAVE_JAX", True)
     shim.CALLS.clear()
     jax_ffi.register()
-    assert len(jax.ffi.registered) == len(jax_ffi._TARGETS) == 22
+    assert len(jax.ffi.registered) == len(jax_ffi._TARGETS) == 24
     return jax
 
 
@@ -79,6 +79,19 @@ def test_coulomb_and_quadrature_rules(jx, mol, cuda_device):
     Jb = rnd(J.shape, cuda_device, 5)
     (Pb,) = pull(Jb)
     assert torch.equal(Pb, ops._eri_jt_raw(Jb, eri))
+    # J and K from one sweep: values, the pullback through both outputs, and the rules of the transposed sweeps (closure)
+    J2, K2 = jax_ffi.coulomb_jk(eri, P)
+    Jk_ref, K_ref = ops._eri_jk_raw(P, eri)
+    assert torch.equal(J2, Jk_ref) and torch.equal(K2, K_ref)
+    f, args = shim.CALLS[-1]
+    _, pull = shim.vjp(f, *args)
+    Kb = rnd(J.shape, cuda_device, 15)
+    (Pb2,) = pull((Jb, Kb))
+    assert torch.equal(Pb2, ops._eri_jt_raw(Jb, eri) + ops._eri_kt_raw(Kb, eri))
+    g, gargs = shim.CALLS[-1]  # the K transpose the pullback just called
+    assert g is not f
+    (back,) = shim.vjp(g, *gargs)[1](P)
+    assert torch.equal(back, K_ref)
     rows = 77
     block = eri.reshape(21 * 21, 21, 21)[40:40 + rows].contiguous()
     Jr = jax_ffi.coulomb_j_rows(block, P)

@@ -153,6 +153,10 @@ def test_eri_sweep(cuda_device, n):
     assert abs(float(EJ) - float(oracle.coulomb_energy(P, eri))) < 1e-11 * abs(float(oracle.coulomb_energy(P, eri)))
     K = ops.coulomb_k(P_d, eri_d)
     assert relerr(K, torch.einsum("pqrt,qt->pr", eri, P)) < RTOL
+    # J and K from ONE pass over the tensor (gdft_eri_jk with K requested); run-to-run reproducible
+    Jf, Kf = ops.coulomb_jk(P_d, eri_d)
+    assert relerr(Jf, oracle.coulomb_potential(P, eri)) < RTOL and torch.equal(Kf, K)
+    assert all(torch.equal(a, b) for a, b in zip(ops.coulomb_jk(P_d, eri_d), (Jf, Kf)))
     # transpose sweep on a NON-symmetric tensor pins the index pairing
     g = torch.Generator().manual_seed(3)
     eri_ns = torch.randn(n, n, n, n, generator=g, dtype=F64)
@@ -163,6 +167,27 @@ def test_eri_sweep(cuda_device, n):
     (got,) = torch.autograd.grad((ops.coulomb_j(Pd, eri_ns.to(dev)) * Jbar.to(dev)).sum(), Pd)
     assert relerr(got, ref) < RTOL
     assert relerr(ops.coulomb_j(P_d, eri_ns.to(dev)), oracle.coulomb_potential(P, eri_ns)) < RTOL
+    # the same for the J+K sweep: values, the VJP through both outputs and the VJP of the VJP, on the non-symmetric tensor
+    Kbar = torch.randn(n, n, generator=g, dtype=F64)
+    Pq = P.clone().requires_grad_(True)
+    Jr, Kr = oracle.coulomb_potential(Pq, eri_ns), torch.einsum("pqrt,qt->pr", eri_ns, Pq)
+    (ref,) = torch.autograd.grad((Jr * Jbar).sum() + (Kr * Kbar).sum(), Pq)
+    (ref_k,) = torch.autograd.grad((torch.einsum("pqrt,qt->pr", eri_ns, Pq) * Kbar).sum(), Pq)
+    Pd = P_d.clone().requires_grad_(True)
+    Jg, Kg = ops.coulomb_jk(Pd, eri_ns.to(dev))
+    assert relerr(Jg.detach(), Jr.detach()) < RTOL and relerr(Kg.detach(), Kr.detach()) < RTOL
+    (got,) = torch.autograd.grad((Jg * Jbar.to(dev)).sum() + (Kg * Kbar.to(dev)).sum(), Pd)
+    assert relerr(got, ref) < RTOL
+    Pd = P_d.clone().requires_grad_(True)
+    (got_k,) = torch.autograd.grad((ops.coulomb_k(Pd, eri_ns.to(dev)) * Kbar.to(dev)).sum(), Pd)
+    assert relerr(got_k, ref_k) < RTOL
+    # K is linear in P: the VJP of its VJP is the sweep itself
+    Kb = Kbar.to(dev).clone().requires_grad_(True)
+    Pd = P_d.clone().requires_grad_(True)
+    (v,) = torch.autograd.grad((ops.coulomb_k(Pd, eri_ns.to(dev)) * Kb).sum(), Pd, create_graph=True)
+    U = torch.randn(n, n, generator=g, dtype=F64)
+    (vv,) = torch.autograd.grad((v * U.to(dev)).sum(), Kb)
+    assert relerr(vv, torch.einsum("pqrt,qt->pr", eri_ns, U)) < RTOL
 
 
 @pytest.mark.parametrize("n,world", [(12, 2), (43, 3), (64, 8)])

@@ -96,6 +96,13 @@ def test_eri_adapters(cuda_device, mol):
     ws, nb = ws_tensor(_lib.OP_ERI_J, 0, n, 0, 0, dev)
     assert xla_call("eri_j_transpose", [eri, Jbar], [Pbar, ws], n=n, ws_bytes=nb) == 0
     assert torch.equal(Pbar, Pref)
+    Jr2, Kr2 = ops._eri_jk_raw(P, eri)
+    J2, K2 = torch.empty_like(Jr2), torch.empty_like(Kr2)
+    assert xla_call("eri_jk", [eri, P], [J2, K2, ws], n=n, ws_bytes=nb) == 0
+    assert torch.equal(J2, Jr2) and torch.equal(K2, Kr2)
+    Pk = torch.empty_like(Pref)
+    assert xla_call("eri_k_transpose", [eri, Jbar], [Pk, ws], n=n, ws_bytes=nb) == 0
+    assert torch.equal(Pk, ops._eri_kt_raw(Jbar, eri))
     rows = 97
     block = eri.reshape(n * n, n, n)[32:32 + rows].contiguous()
     Jr_ref = ops._CoulombJRows.apply(P, block)
@@ -288,6 +295,8 @@ def test_every_call_plan_of_the_jax_binding(cuda_device, mol):
     assert torch.equal(Jm, Jref) and torch.equal(EJ, EJref)
     Jbar = rn(n, n)
     assert torch.equal(go(J.plan_eri_j_transpose(n), [eri, Jbar])[0], ops._eri_jt_raw(Jbar, eri))
+    assert all(torch.equal(x, y) for x, y in zip(go(J.plan_eri_jk(n), [eri, P])[:2], ops._eri_jk_raw(P, eri)))
+    assert torch.equal(go(J.plan_eri_k_transpose(n), [eri, Jbar])[0], ops._eri_kt_raw(Jbar, eri))
     rows = 61
     block = eri.reshape(n * n, n, n)[17:17 + rows].contiguous()
     assert torch.equal(go(J.plan_eri_j_rows(n, rows), [block, P])[0], Jref.reshape(-1)[17:17 + rows])
