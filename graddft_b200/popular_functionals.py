@@ -43,29 +43,33 @@ def lyp_c_e(rho: Array, grad_rho: Array, grad2rho: Array, clip_cte: float = 1e-3
 
 
 # ---- feature builders (popular_functionals.py:270-326): one fused kernel per feature set -------------
+# the per-point feature set (kernel id) behind each functional's `energy_densities`; `fused_xc_spec` reads the same table
+_PW_SET = {"LSDA": "LSDA_X", "B88": "B88_SET", "VWN": "VWN_C", "LYP": "LYP_C", "PW92": "PW92_C", "B3LYP": "B3LYP_SET"}
+
+
 def lsda_density(molecule: Molecule, clip_cte: float = 1e-30, *_, **__) -> Array:
-    return ops.pointwise("LSDA_X", molecule.density(), clip=clip_cte)
+    return ops.pointwise(_PW_SET["LSDA"], molecule.density(), clip=clip_cte)
 
 
 def b88_density(molecule: Molecule, clip_cte: float = 1e-30, *_, **__) -> Array:
-    return ops.pointwise("B88_SET", molecule.density(), molecule.grad_density(), clip=clip_cte)
+    return ops.pointwise(_PW_SET["B88"], molecule.density(), molecule.grad_density(), clip=clip_cte)
 
 
 def vwn_density(molecule: Molecule, clip_cte: float = 1e-30, *_, **__) -> Array:
-    return ops.pointwise("VWN_C", molecule.density(), clip=clip_cte)
+    return ops.pointwise(_PW_SET["VWN"], molecule.density(), clip=clip_cte)
 
 
 def pw92_densities(molecule: Molecule, clip_cte: float = 1e-30, *_, **__) -> Array:
-    return ops.pointwise("PW92_C", molecule.density(), clip=clip_cte)
+    return ops.pointwise(_PW_SET["PW92"], molecule.density(), clip=clip_cte)
 
 
 def lyp_density(molecule: Molecule, clip_cte: float = 1e-30, *_, **__) -> Array:
-    return ops.pointwise("LYP_C", molecule.density(), molecule.grad_density(), None, molecule.lapl_density(), clip=clip_cte)
+    return ops.pointwise(_PW_SET["LYP"], molecule.density(), molecule.grad_density(), None, molecule.lapl_density(), clip=clip_cte)
 
 
 def b3lyp_exhf_densities(molecule: Molecule, clip_cte: float = 1e-30, *_, **__) -> Array:
     """columns [lsda_x, b88_x, vwn_c, lyp_c] -- popular_functionals.py:306-326."""
-    return ops.pointwise("B3LYP_SET", molecule.density(), molecule.grad_density(), None, molecule.lapl_density(), clip=clip_cte)
+    return ops.pointwise(_PW_SET["B3LYP"], molecule.density(), molecule.grad_density(), None, molecule.lapl_density(), clip=clip_cte)
 
 
 def b3lyp_combine(features: Array, ehf: Array) -> Array:
@@ -134,8 +138,9 @@ def fused_xc_spec(functional):
     generic features -> combine -> clip -> quadrature -> autograd chain; None for anything else (user-defined functionals,
     neural functionals).  The rows are the very numbers `coefficients` returns."""
     a0, ax, ac = 0.2, 0.72, 0.81
-    table = ((LSDA, "LSDA_X", (1.0,), None), (B88, "B88_SET", (1.0, 1.0), None), (VWN, "VWN_C", (1.0,), None), (LYP, "LYP_C", (1.0,), None),
-             (PW92, "PW92_C", (1.0,), None), (B3LYP, "B3LYP_SET", (1 - a0, ax, 1 - ac, ac, a0), (0.0,)))
+    table = ((LSDA, _PW_SET["LSDA"], (1.0,), None), (B88, _PW_SET["B88"], (1.0, 1.0), None), (VWN, _PW_SET["VWN"], (1.0,), None),
+             (LYP, _PW_SET["LYP"], (1.0,), None), (PW92, _PW_SET["PW92"], (1.0,), None),
+             (B3LYP, _PW_SET["B3LYP"], (1 - a0, ax, 1 - ac, ac, a0), (0.0,)))
     for fun, name, row, omegas in table:
         if functional is fun:
             return name, row, omegas

@@ -90,8 +90,7 @@ def _fused_xc_build(functional, spec, params, rdm1: Array, atoms: Molecule):
 
     name, row, omegas = spec
     at = atoms.replace(rdm1=rdm1.detach())
-    want_grad = name in ("B88_X", "LYP_C", "B3LYP_SET", "B88_SET")
-    want_lapl = name in ("LYP_C", "B3LYP_SET")
+    want_grad, want_lapl = "grad" in functional.needs, "lapl" in functional.needs  # what the functional's own feature set reads
     flags = GDFT_RHO | (GDFT_GRAD if want_grad else 0) | (GDFT_LAPL if want_lapl else 0) | (GDFT_HF if omegas else 0)
     basis = at.packed_basis.select_chi(at._omega_indices(omegas)) if omegas else at.packed_basis
     with torch.no_grad():

@@ -61,3 +61,27 @@ def test_xla_adapter_dims_layout():
 
     jax_ffi.check_layout()
     assert len(jax_ffi.pack_dims(N=5, n=3)) == _lib.lib().gdft_xla_dims_size()
+
+
+def test_fused_xc_rows_are_the_functionals_own_coefficient_rows():
+    """popular_functionals.fused_xc_spec (host logic of the one-pass per-point kernel): for every closed-form functional the
+    constant row handed to gdft_xc_point_fused is what `Functional.coefficients_for` broadcasts over the columns of the
+    functional's own feature set (grad_dft/functional.py:246-250: einsum "rf,rf->r" with a [1, 1] or [1, F] row), the
+    exact-exchange column last; functionals outside the table take the generic chain."""
+    import torch
+
+    import graddft_b200 as gd
+    from graddft_b200 import _lib
+    from graddft_b200.popular_functionals import fused_xc_spec
+
+    L = _lib.lib()
+    for fun in (gd.LSDA, gd.B88, gd.VWN, gd.LYP, gd.PW92, gd.B3LYP):
+        name, row, omegas = fused_xc_spec(fun)
+        F = int(L.gdft_pointwise_ncols(_lib.PW_IDS[name]))
+        ncols = F + (1 if omegas else 0)
+        assert len(row) == ncols
+        like = torch.empty((5, ncols), dtype=torch.float64)
+        want = fun.coefficients_for(None, None, like)
+        assert tuple(want.shape) == (1, ncols)
+        assert torch.equal(want.cpu().reshape(-1), torch.tensor(row, dtype=torch.float64))
+    assert fused_xc_spec(gd.DM21()) is None
