@@ -100,6 +100,26 @@ def test_predictor(cuda_device, tag):
         close(functional.compute_densities(m), d[f"densities_{name}"], 1e-10)
 
 
+@pytest.mark.parametrize("tag,names", [("n43", ("LSDA", "B88", "VWN", "LYP", "PW92", "B3LYP")), ("n97", ("B88", "B3LYP"))])
+def test_predictor_at_named_widths(cuda_device, tag, names):
+    """energy_predictor against the reference's own source at 43 AOs (H2O / def2-TZVP) and 97 AOs: other tile classes of K1 / K2,
+    the one-pass per-point kernel and the packed rep_tensor sweep than the n <= 12 vectors exercise.  Inputs are regenerated from
+    the seed and verified against stored checksums (tests/golden/make_golden_wide.py)."""
+    from graddft_b200.synthetic import synthetic_molecule
+
+    d = load("predictor_wide.npz")
+    N, n, seed = (int(x) for x in d[f"{tag}_shape"])
+    mol = synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0)
+    sums = torch.tensor([float(mol[k].double().sum()) for k in ("ao", "grad_ao", "rdm1", "weights", "rep_tensor", "chi", "h1e")], dtype=torch.float64)
+    assert torch.allclose(sums, d[f"{tag}_checksums"], rtol=1e-12, atol=0), "synthetic_molecule no longer reproduces the golden inputs"
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    for name in names:
+        for _ in range(2):  # the second call goes through the packed rep_tensor (packed at its second use)
+            e, f = gd.energy_predictor(getattr(gd, name))(None, m)
+            assert abs(float(e) - float(d[f"{tag}_energy_{name}"])) < 1e-8, name     # Ha (BASELINE.json)
+            close(f, d[f"{tag}_fock_{name}"], 1e-7)                                    # relative (BASELINE.json)
+
+
 def test_predictor_dm21(cuda_device):
     d = load("predictor_dm21.npz")
     m = molecule(d, cuda_device)

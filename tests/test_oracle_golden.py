@@ -99,6 +99,30 @@ def test_predictor(tag):
     close(f, d["fock_B3LYP"], rtol=1e-9, atol_scale=1e-12)
 
 
+def _wide_case(d, tag):
+    """Regenerates the inputs of a predictor_wide.npz case (they are not stored) and checks them against the stored checksums."""
+    from graddft_b200.synthetic import synthetic_molecule
+
+    N, n, seed = (int(x) for x in d[f"{tag}_shape"])
+    mol = synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0)
+    sums = torch.tensor([float(mol[k].double().sum()) for k in ("ao", "grad_ao", "rdm1", "weights", "rep_tensor", "chi", "h1e")], dtype=torch.float64)
+    assert torch.allclose(sums, d[f"{tag}_checksums"], rtol=1e-12, atol=0), "synthetic_molecule no longer reproduces the golden inputs"
+    return mol
+
+
+def test_predictor_at_the_h2o_width():
+    """The restatement against the reference's own energy_predictor at n = 43 (tests/golden/make_golden_wide.py)."""
+    d = load("predictor_wide.npz")
+    mol = _wide_case(d, "n43")
+    for name in ("LSDA", "B88", "VWN", "LYP", "PW92"):
+        e, f = oracle.predict_semilocal(mol, name)
+        assert abs(float(e) - float(d[f"n43_energy_{name}"])) < 1e-9, name
+        close(f, d[f"n43_fock_{name}"], rtol=1e-9, atol_scale=1e-12)
+    e, f = oracle.predict_b3lyp(mol)
+    assert abs(float(e) - float(d["n43_energy_B3LYP"])) < 1e-9
+    close(f, d["n43_fock_B3LYP"], rtol=1e-9, atol_scale=1e-12)
+
+
 def test_predictor_dm21():
     d = load("predictor_dm21.npz")
     mol = {k: v for k, v in d.items() if not k.startswith(("energy_", "fock_", "param_", "out_"))}
