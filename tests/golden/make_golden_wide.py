@@ -1,7 +1,7 @@
 """tests/golden/predictor_wide.npz: energy_predictor of the reference's own source files (imported from /root/reference,
 unmodified, on the torch-backed jax stand-in of jaxshim.py, like make_golden.py) at the widths BASELINE.json names for the
 small configurations -- 43 AOs (H2O / def2-TZVP) and 97 AOs -- where the CUDA kernels run other tile classes than at the n <= 12
-of predictor_{a,b}.npz.  The inputs are NOT stored (a 97^4 rep_tensor is 708 MB): they are `synthetic_molecule(N, n, seed)`,
+of predictor_{a,b}.npz -- and tests/golden/scf_wide.npz: diff_scf_loop (B3LYP, 3 DIIS cycles; B88, 5) and the DM21 predictor at 43 AOs.  The inputs are NOT stored (a 97^4 rep_tensor is 708 MB): they are `synthetic_molecule(N, n, seed)`,
 which the test regenerates; a few input checksums are stored so that a drifting generator fails loudly instead of silently
 comparing different molecules.
 
@@ -39,6 +39,33 @@ def main():
             print(tag, name, float(e))
     np.savez_compressed(HERE / "predictor_wide.npz", **d)
     print((HERE / "predictor_wide.npz").stat().st_size)
+
+    # ---- the DIIS loop (evaluate.py:917-1038) and the DM21 predictor at 43 AOs -> scf_wide.npz ------------------------------
+    import oracle
+
+    d = {}
+    N, n, seed = 3000, 43, 2143
+    mol = mg.synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0)
+    m = mg.ref_molecule(mol)
+    d["shape"], d["checksums"] = np.array([N, n, seed]), checksums(mol)
+    for name, cycles in (("B3LYP", 3), ("B88", 5)):
+        out = mg.gd.diff_scf_loop(getattr(mg.gd, name), cycles=cycles)(None, m)
+        d[f"diis_energy_{name}_{cycles}"], d[f"diis_rdm1_{name}_{cycles}"], d[f"diis_fock_{name}_{cycles}"] = mg.np_(out.energy), mg.np_(out.rdm1), mg.np_(out.fock)
+        print("scf", name, cycles, float(out.energy))
+    flat = oracle.dm21_mlp_init(width=32, n_layers=3, seed=2143)
+    tree = {}
+    for k, v in flat.items():
+        layer, leaf = k.split(".")
+        tree.setdefault(layer, {})[leaf] = mg.J(v)
+    dm21 = mg.gd.DM21()
+    dm21.layer_widths = [32, 32, 32]
+    e, fock = mg.gd.energy_predictor(dm21)({"params": tree}, m)
+    for k, v in flat.items():
+        d["param_" + k] = mg.np_(v)
+    d["energy_DM21"], d["fock_DM21"] = mg.np_(e), mg.np_(fock)
+    print("DM21", float(e))
+    np.savez_compressed(HERE / "scf_wide.npz", **d)
+    print((HERE / "scf_wide.npz").stat().st_size)
 
 
 if __name__ == "__main__":

@@ -152,6 +152,32 @@ def test_scf_loops(cuda_device):
     close(out.rdm1, d["simple_rdm1_LSDA_3"], 1e-6, 1e-8)
 
 
+def test_scf_loop_and_dm21_at_the_h2o_width(cuda_device):
+    """diff_scf_loop with B3LYP (exact-exchange route, one-pass per-point kernel, K12 DIIS stage, warm-started Jacobi) and B88, its
+    CUDA-graph replay, and the DM21 predictor, against the reference's own source at 43 AOs (scf_wide.npz)."""
+    from graddft_b200.evaluate import diff_scf_loop, make_jitted_scf_loop
+    from graddft_b200.synthetic import synthetic_molecule
+
+    d = load("scf_wide.npz")
+    N, n, seed = (int(x) for x in d["shape"])
+    mol = synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0)
+    sums = torch.tensor([float(mol[k].double().sum()) for k in ("ao", "grad_ao", "rdm1", "weights", "rep_tensor", "chi", "h1e")], dtype=torch.float64)
+    assert torch.allclose(sums, d["checksums"], rtol=1e-12, atol=0), "synthetic_molecule no longer reproduces the golden inputs"
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    tol = 1e-6 / 627.50947  # tests/integration/molecules/test_predict_B88.py:82-109: 1e-6 kcal/mol
+    for name, cycles in (("B3LYP", 3), ("B88", 5)):
+        for make in (diff_scf_loop, make_jitted_scf_loop):
+            with torch.no_grad():
+                out = make(getattr(gd, name), cycles=cycles)(None, m)
+            assert abs(float(out.energy) - float(d[f"diis_energy_{name}_{cycles}"])) < tol, (name, make.__name__)
+            close(out.rdm1, d[f"diis_rdm1_{name}_{cycles}"], 1e-6, 1e-8)
+            close(out.fock, d[f"diis_fock_{name}_{cycles}"], 1e-6, 1e-8)
+    params = {k[len("param_"):]: v.to(cuda_device) for k, v in d.items() if k.startswith("param_")}
+    e, f = gd.energy_predictor(gd.DM21(layer_widths=(32, 32, 32)))(params, m)
+    assert abs(float(e) - float(d["energy_DM21"])) < 1e-8
+    close(f, d["fock_DM21"], 1e-7)
+
+
 def test_jitted_scf_loop_is_the_eager_loop(cuda_device):
     """make_jitted_scf_loop (CUDA-graph capture of diff_scf_loop, the stand-in for jax.jit, evaluate.py:917) replays to the
     eager result bit for bit, re-reads rdm1 in place on every replay, and falls back to eager when gradients are asked."""

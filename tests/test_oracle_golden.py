@@ -123,6 +123,26 @@ def test_predictor_at_the_h2o_width():
     close(f, d["n43_fock_B3LYP"], rtol=1e-9, atol_scale=1e-12)
 
 
+def test_scf_loop_and_dm21_at_the_h2o_width():
+    """diff_scf_loop (B3LYP: the hybrid route inside the DIIS loop; B88) and the DM21 predictor restated, against the reference's
+    own evaluate.py / train.py at n = 43 (tests/golden/make_golden_wide.py -> scf_wide.npz)."""
+    from graddft_b200.synthetic import synthetic_molecule
+
+    d = load("scf_wide.npz")
+    N, n, seed = (int(x) for x in d["shape"])
+    mol = synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0)
+    sums = torch.tensor([float(mol[k].double().sum()) for k in ("ao", "grad_ao", "rdm1", "weights", "rep_tensor", "chi", "h1e")], dtype=torch.float64)
+    assert torch.allclose(sums, d["checksums"], rtol=1e-12, atol=0)
+    for name, cycles, pred in (("B3LYP", 3, oracle.predict_b3lyp), ("B88", 5, lambda m: oracle.predict_semilocal(m, "B88"))):
+        e, out = oracle.diff_scf_loop_energy(mol, pred, cycles)
+        assert abs(float(e) - float(d[f"diis_energy_{name}_{cycles}"])) < 1e-9, name
+        close(out["rdm1"], d[f"diis_rdm1_{name}_{cycles}"], rtol=1e-7, atol_scale=1e-9)
+    params = {k[len("param_"):]: v for k, v in d.items() if k.startswith("param_")}
+    e, f = oracle.predict_dm21(mol, params)
+    assert abs(float(e) - float(d["energy_DM21"])) < 1e-9
+    close(f, d["fock_DM21"], rtol=1e-8, atol_scale=1e-11)
+
+
 def test_predictor_dm21():
     d = load("predictor_dm21.npz")
     mol = {k: v for k, v in d.items() if not k.startswith(("energy_", "fock_", "param_", "out_"))}
