@@ -1,7 +1,7 @@
 """tests/golden/predictor_wide.npz: energy_predictor of the reference's own source files (imported from /root/reference,
 unmodified, on the torch-backed jax stand-in of jaxshim.py, like make_golden.py) at the widths BASELINE.json names for the
 small configurations -- 43 AOs (H2O / def2-TZVP) and 97 AOs -- where the CUDA kernels run other tile classes than at the n <= 12
-of predictor_{a,b}.npz -- and tests/golden/scf_wide.npz: diff_scf_loop (B3LYP, 3 DIIS cycles; B88, 5) and the DM21 predictor at 43 AOs.  The inputs are NOT stored (a 97^4 rep_tensor is 708 MB): they are `synthetic_molecule(N, n, seed)`,
+of predictor_{a,b}.npz -- and tests/golden/scf_wide.npz: diff_scf_loop (B3LYP, 3 DIIS cycles; B88, 5) and the DM21 predictor at 43 AOs; and tests/golden/train_batch.npz: mse_energy_loss of a three-molecule batch with its parameter gradient.  The inputs are NOT stored (a 97^4 rep_tensor is 708 MB): they are `synthetic_molecule(N, n, seed)`,
 which the test regenerates; a few input checksums are stored so that a drifting generator fails loudly instead of silently
 comparing different molecules.
 
@@ -66,6 +66,43 @@ def main():
     print("DM21", float(e))
     np.savez_compressed(HERE / "scf_wide.npz", **d)
     print((HERE / "scf_wide.npz").stat().st_size)
+
+    # ---- training batch (train.py:480-535 mse_energy_loss over non_scf_predictor, evaluate.py:88-126) -> train_batch.npz ------
+    # the loss of the reference's own source and its gradient w.r.t. the network parameters (torch autograd through the stand-in,
+    # where jax.grad would act), for three molecules of different sizes and a DM21-shaped network with seeded weights
+    tr = sys.modules["grad_dft.train"]
+    d = {}
+    shapes = [(900, 9, 3101), (1200, 14, 3102), (700, 7, 3103)]
+    atom_index = [[8, 1, 1], [6, 1, 1, 1, 1], [7, 1, 1, 1]]
+    mols = [mg.synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0) for N, n, seed in shapes]
+    ms = [mg.ref_molecule(mol).replace(atom_index=mg.J(torch.tensor(z, dtype=torch.int64))) for mol, z in zip(mols, atom_index)]
+    d["shapes"] = np.array(shapes)
+    d["atom_index"] = np.array([z + [0] * (5 - len(z)) for z in atom_index])
+    d["checksums"] = np.stack([checksums(mol) for mol in mols])
+    truths = torch.tensor([-70.0, -40.0, -55.0], dtype=torch.float64)
+    d["truths"] = mg.np_(truths)
+    flat = oracle.dm21_mlp_init(width=32, n_layers=3, seed=3100)
+    leaves = {k: mg.J(v.clone().requires_grad_(True)) for k, v in flat.items()}
+    tree = {}
+    for k, v in leaves.items():
+        layer, leaf = k.split(".")
+        tree.setdefault(layer, {})[leaf] = v
+    dm21 = mg.gd.DM21()
+    dm21.layer_widths = [32, 32, 32]
+    predictor = sys.modules["grad_dft.evaluate"].non_scf_predictor(dm21)
+    with torch.enable_grad():
+        for norm in (True, False):
+            loss = tr.mse_energy_loss({"params": tree}, predictor, ms, mg.J(truths), norm)
+            grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+            tag = "norm" if norm else "plain"
+            d[f"loss_{tag}"] = mg.np_(loss)
+            for k, g in zip(leaves, grads):
+                d[f"grad_{tag}_{k}"] = mg.np_(g if g is not None else torch.zeros_like(leaves[k]))
+            print("train", tag, float(loss))
+    for k, v in flat.items():
+        d["param_" + k] = mg.np_(v)
+    np.savez_compressed(HERE / "train_batch.npz", **d)
+    print((HERE / "train_batch.npz").stat().st_size)
 
 
 if __name__ == "__main__":

@@ -178,6 +178,33 @@ def test_scf_loop_and_dm21_at_the_h2o_width(cuda_device):
     close(f, d["fock_DM21"], 1e-7)
 
 
+def test_training_batch_loss_and_parameter_gradient(cuda_device):
+    """The non-SCF training path (train.py:480-535 over evaluate.py:88-126) against the reference's own source: loss of a
+    three-molecule batch and its gradient w.r.t. the parameters of a DM21-shaped network (train_batch.npz), through the public
+    API -- per-molecule and through the batched entry the loss uses for more than one molecule."""
+    from graddft_b200.synthetic import synthetic_molecule
+
+    d = load("train_batch.npz")
+    ms = []
+    for (N, n, seed), z, sums in zip(d["shapes"].tolist(), d["atom_index"].tolist(), d["checksums"]):
+        mol = synthetic_molecule(int(N), int(n), n_omega=2, seed=int(seed), mask_frac=0.0)
+        got = torch.tensor([float(mol[k].double().sum()) for k in ("ao", "grad_ao", "rdm1", "weights", "rep_tensor", "chi", "h1e")], dtype=torch.float64)
+        assert torch.allclose(got, sums, rtol=1e-12, atol=0), "synthetic_molecule no longer reproduces the golden inputs"
+        mol["atom_index"] = torch.tensor([a for a in z if a > 0], dtype=torch.int64)
+        ms.append(gd.molecule_from_tensors(mol, cuda_device))
+    fun = gd.DM21(layer_widths=(32, 32, 32))
+    predictor = gd.non_scf_predictor(fun)
+    truths = d["truths"].to(cuda_device)
+    for tag, norm in (("norm", True), ("plain", False)):
+        params = {k[len("param_"):]: v.to(cuda_device).requires_grad_(True) for k, v in d.items() if k.startswith("param_")}
+        loss = gd.mse_energy_loss(params, predictor, ms, truths, norm)
+        assert abs(float(loss.detach()) - float(d[f"loss_{tag}"])) < 1e-9 * abs(float(d[f"loss_{tag}"])), tag
+        for k, g in zip(params, torch.autograd.grad(loss, list(params.values()), allow_unused=True)):
+            ref = d[f"grad_{tag}_{k}"]
+            g = g.cpu() if g is not None else torch.zeros_like(ref)
+            assert float((g - ref).abs().max()) <= 1e-7 * float(ref.abs().max()) + 1e-13, (tag, k)
+
+
 def test_jitted_scf_loop_is_the_eager_loop(cuda_device):
     """make_jitted_scf_loop (CUDA-graph capture of diff_scf_loop, the stand-in for jax.jit, evaluate.py:917) replays to the
     eager result bit for bit, re-reads rdm1 in place on every replay, and falls back to eager when gradients are asked."""

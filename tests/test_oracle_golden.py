@@ -143,6 +143,43 @@ def test_scf_loop_and_dm21_at_the_h2o_width():
     close(f, d["fock_DM21"], rtol=1e-8, atol_scale=1e-11)
 
 
+def _train_batch(d):
+    from graddft_b200.synthetic import synthetic_molecule
+
+    mols = []
+    for (N, n, seed), z, sums in zip(d["shapes"].tolist(), d["atom_index"].tolist(), d["checksums"]):
+        mol = synthetic_molecule(int(N), int(n), n_omega=2, seed=int(seed), mask_frac=0.0)
+        got = torch.tensor([float(mol[k].double().sum()) for k in ("ao", "grad_ao", "rdm1", "weights", "rep_tensor", "chi", "h1e")], dtype=torch.float64)
+        assert torch.allclose(got, sums, rtol=1e-12, atol=0), "synthetic_molecule no longer reproduces the golden inputs"
+        mol["atom_index"] = torch.tensor([a for a in z if a > 0], dtype=torch.int64)
+        mols.append(mol)
+    return mols
+
+
+def test_training_batch_loss_and_parameter_gradient():
+    """mse_energy_loss over non_scf_predictor (train.py:480-535, evaluate.py:88-126) of the reference's own source for a
+    three-molecule batch and a DM21-shaped network, with its gradient w.r.t. the parameters (train_batch.npz): the restatement
+    (energy of the fixed density + torch autograd) reproduces both, with and without the electron-number normalisation."""
+    d = load("train_batch.npz")
+    mols = _train_batch(d)
+    flat = {k[len("param_"):]: v for k, v in d.items() if k.startswith("param_")}
+    for tag, norm in (("norm", True), ("plain", False)):
+        pl = {k: v.clone().requires_grad_(True) for k, v in flat.items()}
+        loss = 0.0
+        for m, t in zip(mols, d["truths"]):
+            e = oracle.xc_energy_of_rdm1(m["rdm1"], m, "DM21", params=pl) + oracle.nonXC(m["rdm1"].sum(0), m["h1e"], m["rep_tensor"], m["nuclear_repulsion"])
+            diff = e - t
+            if norm:
+                diff = diff / m["atom_index"].sum()
+            loss = loss + diff ** 2
+        loss = loss / len(mols)
+        assert abs(float(loss.detach()) - float(d[f"loss_{tag}"])) < 1e-10 * abs(float(d[f"loss_{tag}"]))
+        for k, g in zip(pl, torch.autograd.grad(loss, list(pl.values()), allow_unused=True)):
+            ref = d[f"grad_{tag}_{k}"]
+            g = g if g is not None else torch.zeros_like(ref)
+            assert float((g - ref).abs().max()) <= 1e-8 * float(ref.abs().max()) + 1e-14, (tag, k)
+
+
 def test_predictor_dm21():
     d = load("predictor_dm21.npz")
     mol = {k: v for k, v in d.items() if not k.startswith(("energy_", "fock_", "param_", "out_"))}
