@@ -205,6 +205,34 @@ def test_training_batch_loss_and_parameter_gradient(cuda_device):
             assert float((g - ref).abs().max()) <= 1e-7 * float(ref.abs().max()) + 1e-13, (tag, k)
 
 
+def test_parameter_gradient_through_the_scf_loops(cuda_device):
+    """Training through the SCF loop (evaluate.py:917-1038 and 257-352 under jax.grad) against the reference's own source for the
+    hybrid DM21 functional (scf_grad.npz): energy after two cycles and its gradient w.r.t. every network parameter -- second-order
+    per-point kernels, the transposed density kernels, the eigh VJP and DIIS on the CUDA path."""
+    from graddft_b200.synthetic import synthetic_molecule
+
+    d = load("scf_grad.npz")
+    N, n, seed = (int(x) for x in d["shape"])
+    mol = synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0)
+    mol["h1e"] = torch.diag(torch.linspace(-8.0, 8.0, n, dtype=torch.float64)) + 0.05 * mol["h1e"]  # make_golden_wide.py::gapped
+    mol["rep_tensor"] = 0.05 * mol["rep_tensor"]
+    mol["s1e"] = torch.eye(n, dtype=torch.float64) + 0.2 * (mol["s1e"] - torch.eye(n, dtype=torch.float64))
+    sums = torch.tensor([float(mol[k].double().sum()) for k in ("ao", "grad_ao", "rdm1", "weights", "rep_tensor", "chi", "h1e")], dtype=torch.float64)
+    assert torch.allclose(sums, d["checksums"], rtol=1e-12, atol=0), "synthetic_molecule no longer reproduces the golden inputs"
+    m = gd.molecule_from_tensors(mol, cuda_device)
+    fun = gd.DM21(layer_widths=(8, 8))
+    for tag, make in (("diis", lambda: gd.diff_scf_loop(fun, cycles=2)), ("simple", lambda: gd.diff_simple_scf_loop(fun, cycles=2))):
+        params = {k[len("param_"):]: v.to(cuda_device).requires_grad_(True) for k, v in d.items() if k.startswith("param_")}
+        e = make()(params, m).energy
+        assert abs(float(e.detach()) - float(d[f"energy_{tag}"])) < 1e-7, tag
+        grads = torch.autograd.grad(e, list(params.values()), allow_unused=True)
+        scale = max(float(d[f"grad_{tag}_{k}"].abs().max()) for k in params)
+        for k, g in zip(params, grads):
+            ref = d[f"grad_{tag}_{k}"]
+            g = g.cpu() if g is not None else torch.zeros_like(ref)
+            assert float((g - ref).abs().max()) < 1e-6 * scale, (tag, k)
+
+
 def test_jitted_scf_loop_is_the_eager_loop(cuda_device):
     """make_jitted_scf_loop (CUDA-graph capture of diff_scf_loop, the stand-in for jax.jit, evaluate.py:917) replays to the
     eager result bit for bit, re-reads rdm1 in place on every replay, and falls back to eager when gradients are asked."""

@@ -180,6 +180,39 @@ def test_training_batch_loss_and_parameter_gradient():
             assert float((g - ref).abs().max()) <= 1e-8 * float(ref.abs().max()) + 1e-14, (tag, k)
 
 
+def _gapped(mol):
+    """tests/golden/make_golden_wide.py::gapped."""
+    n = mol["h1e"].shape[-1]
+    mol["h1e"] = torch.diag(torch.linspace(-8.0, 8.0, n, dtype=torch.float64)) + 0.05 * mol["h1e"]
+    mol["rep_tensor"] = 0.05 * mol["rep_tensor"]
+    mol["s1e"] = torch.eye(n, dtype=torch.float64) + 0.2 * (mol["s1e"] - torch.eye(n, dtype=torch.float64))
+    return mol
+
+
+def test_parameter_gradient_through_the_scf_loops():
+    """jax.grad through diff_scf_loop / diff_simple_scf_loop (evaluate.py:917-1038, 257-352) of the reference's own source for the
+    hybrid DM21 functional (scf_grad.npz): the traced restatement -- stop_gradients, safe-eigh VJP and DIIS included -- gives the
+    same energy and the same gradient w.r.t. every parameter."""
+    from graddft_b200.synthetic import synthetic_molecule
+
+    d = load("scf_grad.npz")
+    N, n, seed = (int(x) for x in d["shape"])
+    mol = _gapped(synthetic_molecule(N, n, n_omega=2, seed=seed, mask_frac=0.0))
+    sums = torch.tensor([float(mol[k].double().sum()) for k in ("ao", "grad_ao", "rdm1", "weights", "rep_tensor", "chi", "h1e")], dtype=torch.float64)
+    assert torch.allclose(sums, d["checksums"], rtol=1e-12, atol=0)
+    flat = {k[len("param_"):]: v for k, v in d.items() if k.startswith("param_")}
+    for tag, loop in (("diis", oracle.diff_scf_loop_energy), ("simple", oracle.diff_simple_scf_loop_energy)):
+        pl = {k: v.clone().requires_grad_(True) for k, v in flat.items()}
+        e, _ = loop(mol, lambda mm: oracle.predict_dm21_traced(mm, pl), 2)
+        assert abs(float(e.detach()) - float(d[f"energy_{tag}"])) < 1e-9, tag
+        grads = torch.autograd.grad(e, list(pl.values()), allow_unused=True)
+        scale = max(float(d[f"grad_{tag}_{k}"].abs().max()) for k in pl)
+        for k, g in zip(pl, grads):
+            ref = d[f"grad_{tag}_{k}"]
+            g = g if g is not None else torch.zeros_like(ref)
+            assert float((g - ref).abs().max()) < 1e-7 * scale, (tag, k)
+
+
 def test_predictor_dm21():
     d = load("predictor_dm21.npz")
     mol = {k: v for k, v in d.items() if not k.startswith(("energy_", "fock_", "param_", "out_"))}
