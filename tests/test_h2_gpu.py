@@ -76,3 +76,22 @@ def test_b3lyp_and_scf_loop_on_h2(h2):
     # n = 2 through the jitted SCF driver: sigma_g is fixed by symmetry, so the density must stay put and the energy too
     out = gd.make_jitted_scf_loop(gd.B3LYP, cycles=4)(None, m)
     assert abs(float(out.energy if hasattr(out, "energy") else out[0]) - float(e)) < 1e-8
+
+
+def test_exchange_energy_from_the_rep_tensor_sweep(h2):
+    """The exchange pairing of the one-pass J+K sweep (gdft_eri_jk with K) on a real molecule: E_x = -1/2 sum_s Tr(D_s K[D_s])
+    with K[D]_pr = sum_qt (pq|rt) D_qt equals the closed-form exact-exchange energy, i.e. what the chi route integrates on the
+    grid; J of the same call is the Coulomb matrix, and E_J + E_x closes the RHF energy."""
+    from graddft_b200 import ops
+
+    mol, exp, m = h2
+    e_x, e_j = 0.0, None
+    for s in range(2):
+        J, K = ops.coulomb_jk(m.rdm1[s].contiguous(), m.rep_tensor)
+        e_x += -0.5 * float((m.rdm1[s] * K).sum())
+        assert float((K.cpu() - torch.einsum("pqrt,qt->pr", mol["rep_tensor"], mol["rdm1"][s])).abs().max()) < 1e-13
+        assert float((J.cpu() - torch.einsum("pqrt,rt->pq", mol["rep_tensor"], mol["rdm1"][s])).abs().max()) < 1e-13
+    assert abs(e_x - exp["E_x_HF"]) < 1e-10
+    ehf = m.HF_energy_density([0.0])
+    assert abs(e_x - float((ehf[0] * m.grid.weights).sum())) < 1e-7  # the chi route's quadrature of the same energy
+    assert abs(float(m.nonXC()) + e_x - exp["E_RHF"]) < 1e-9
